@@ -1,0 +1,232 @@
+/*
+ * leven_compute.h -- C ABI of the B200-native chunk-meshing path.
+ *
+ * This is the drop-in boundary: every entry point replaces one symbol of the
+ * reference's compute interface, leven/src/compute.h:12-81 (cited per
+ * function below; paths are relative to the reference tree).  Plain pointers
+ * and sizes only; no C++, CUDA or torch types cross it.  The header-only C++
+ * shim include/leven_compute.hpp rebuilds the reference's own
+ * Compute_MeshGenContext class on top of it; INTEGRATION.md shows the
+ * reference-side change.
+ *
+ * Conventions (same as the reference):
+ *   - return value: 0 = success, negative = failure (LVN_* below; the
+ *     reference returns OpenCL codes the same way and its callers test < 0,
+ *     clipmap.cpp:379).
+ *   - min / size are world units; a voxel is LEAF_SIZE_SCALE (4) world units
+ *     at LOD0 (volume_constants.h:7-8); a 64^3 chunk has size 256.
+ *   - not thread-safe: one caller at a time per process, as in the reference
+ *     (compute.cpp:168-191, volume.cpp:68-113).
+ *   - there is no CPU fallback: every call fails with LVN_ERR_NO_DEVICE when
+ *     no CUDA device is usable.
+ */
+#ifndef LEVEN_COMPUTE_H
+#define LEVEN_COMPUTE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVN_SUCCESS              0
+#define LVN_CL_ERROR             (-99999)  /* compute.h:12, non-OpenCL failure */
+#define LVN_ERR_NO_DEVICE        (-1)      /* == CL_DEVICE_NOT_FOUND */
+#define LVN_ERR_OUT_OF_MEMORY    (-4)      /* == CL_MEM_OBJECT_ALLOCATION_FAILURE */
+#define LVN_ERR_INVALID_VALUE    (-30)     /* == CL_INVALID_VALUE */
+#define LVN_ERR_NOT_INITIALISED  (-34)     /* == CL_INVALID_CONTEXT */
+#define LVN_ERR_CAPACITY         (-61)     /* == CL_INVALID_BUFFER_SIZE: caller arena too small
+                                              (the reference asserts, compute_octree.cpp:235-236) */
+#define LVN_ERR_CUDA             (-9999)   /* a CUDA runtime call failed; see lvn_last_cuda_error */
+
+#define LVN_MATERIAL_NONE 200              /* volume_materials.h:7 */
+#define LVN_MATERIAL_AIR  201              /* volume_materials.h:8 */
+#define LVN_LEAF_SIZE_SCALE 4              /* volume_constants.h:7-8 */
+
+/* ---- PODs shared with the callers (layouts are the reference's) -------- */
+
+/* CSGOperationInfo, compute.h:16-24 (== CSGOperation, apply_csg_operation.cl:5-14) */
+typedef struct lvn_csg_operation_info {
+    int32_t type;          /* 0 = add, 1 = subtract */
+    int32_t brushShape;    /* RenderShape: 0 = cube, 1 = sphere (render_types.h:11-20) */
+    int32_t material;
+    float   rotateY;       /* radians */
+    float   origin[4];     /* voxel units: world/4 + 0.5 (clipmap.cpp:1628) */
+    float   dimensions[4]; /* half extents, voxel units; sphere radius = dimensions[0] */
+} lvn_csg_operation_info;
+
+/* SeamNodeInfo, compute.h:26-31 */
+typedef struct lvn_seam_node_info {
+    int32_t localspaceMin[4];   /* xyz in [0, V); w = (dominantMaterial << 8) | cornerMask */
+    float   position[4];
+    float   normal[4];
+} lvn_seam_node_info;
+
+/* MeshVertex, render_types.h:24-39 */
+typedef struct lvn_mesh_vertex { float xyz[4], normal[4], colour[4]; } lvn_mesh_vertex;
+/* MeshTriangle, render_types.h:42-58 */
+typedef struct lvn_mesh_triangle { int32_t indices_[3]; } lvn_mesh_triangle;
+/* AABB, aabb.h:5-96 (data members only) */
+typedef struct lvn_aabb { int32_t min[3], max[3]; } lvn_aabb;
+
+/* ---- process-wide state ------------------------------------------------- */
+
+/* new: choose the CUDA device before lvn_compute_initialise (one process per GPU) */
+int lvn_compute_set_device(int cudaDevice);
+
+/* Compute_Initialise, compute.h:35 (compute.cpp:195-234) */
+int lvn_compute_initialise(int noiseSeed, unsigned int defaultMaterial, int numCSGBrushes);
+/* Compute_Shutdown, compute.h:36 (a no-op in the reference; frees the device state here) */
+int lvn_compute_shutdown(void);
+/* Compute_SetNoiseSeed, compute.h:38 (compute_density_field.cpp:129-134).  The 512-entry
+ * shuffle uses mt19937(seed) + Fisher-Yates (documented in DESIGN.md) because the reference's
+ * std::shuffle(std::default_random_engine) is implementation-defined. */
+int lvn_compute_set_noise_seed(int noiseSeed);
+/* new: feed the exact 256x256 RGBA8 permutation image (row i, column j at ((i*256)+j)*4,
+ * compute_density_field.cpp:101-113) produced by any other implementation */
+int lvn_compute_set_noise_image(const uint8_t *rgba /* 262144 bytes */);
+int lvn_compute_get_noise_image(uint8_t *rgba /* 262144 bytes */);
+/* new: density function selector.  0 = the reference terrain (noise.cl:225-268),
+ * 1 = BASELINE.json config 4 dense-stress field (ridged fBm over snoise3, simplex.cl:159-230) */
+int lvn_compute_set_density_function(int kind, float param);
+/* Compute_StoreCSGOperation / Compute_ClearCSGOperations, compute.h:39-40 */
+int lvn_compute_store_csg_operation(const lvn_csg_operation_info *op, const lvn_aabb *aabb);
+int lvn_compute_clear_csg_operations(void);
+/* GetCLErrorString, compute.h:81 */
+const char *lvn_error_string(int error);
+const char *lvn_last_cuda_error(void);
+
+/* ---- Compute_MeshGenContext, compute.h:46-77 ----------------------------- */
+
+typedef struct lvn_meshgen lvn_meshgen;
+
+/* Compute_MeshGenContext::create, compute.h:50; NULL on failure */
+lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk);
+/* new: the reference never destroys contexts */
+void lvn_meshgen_destroy(lvn_meshgen *ctx);
+/* voxelsPerChunk, compute.h:52 */
+int lvn_meshgen_voxels_per_chunk(const lvn_meshgen *ctx);
+
+/* applyCSGOperations, compute.h:54-57 (compute_csg.cpp:224-242) */
+int lvn_meshgen_apply_csg_operations(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
+                                     const int32_t clipmapNodeMin[3], int clipmapNodeSize);
+/* freeChunkOctree, compute.h:59-61 (compute_octree.cpp:379-387) */
+int lvn_meshgen_free_chunk_octree(lvn_meshgen *ctx, const int32_t min[3], int size);
+/* isChunkEmpty, compute.h:63-66.  *isEmpty = 1 when the chunk has no surface crossing (the
+ * reference's dead code returns the inverted flag, compute_density_field.cpp:285,296) */
+int lvn_meshgen_is_chunk_empty(lvn_meshgen *ctx, const int32_t min[3], int size, int *isEmpty);
+
+/* generateChunkMesh, compute.h:68-72 (compute_octree.cpp:351-375).  Caller-owned buffers
+ * (MeshBuffer::vertices/triangles, render_types.h:70-90; the seam std::vector's storage).
+ * Returns LVN_ERR_CAPACITY, with the needed counts in *numX, when a buffer is too small. */
+int lvn_meshgen_generate_chunk_mesh(lvn_meshgen *ctx, const int32_t min[3], int clipmapNodeSize,
+                                    lvn_mesh_vertex *vertices, int vertexCapacity, int *numVertices,
+                                    lvn_mesh_triangle *triangles, int triangleCapacity, int *numTriangles,
+                                    lvn_seam_node_info *seamNodes, int seamCapacity, int *numSeamNodes);
+
+/* ---- new: batch entry points (the 512 / 4096-chunk configurations) ------- */
+
+typedef struct lvn_chunk_result {
+    int32_t numEdges, numVertices, numTriangles, numSeamNodes;
+    int32_t vertexOffset, triangleOffset, seamOffset;   /* element offsets into the arenas */
+    int32_t status;                                     /* 0 or a negative LVN_* code */
+} lvn_chunk_result;
+
+/* One pass of the whole path over nChunks independent chunks (chunkMinSize = 4 ints per chunk:
+ * min.x, min.y, min.z, size).  Same per-chunk results as generateChunkMesh on cold octree
+ * caches; does not read or fill the octree cache, does honour CSG-edited density fields.
+ * Host arenas (pinned memory recommended); results[i] addresses chunk i's slices. */
+int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                               lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                               lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                               lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                               lvn_chunk_result *results);
+
+/* Same pass, results left resident in HBM (arenas owned by ctx, valid until the next call). */
+typedef struct lvn_batch_device_view {
+    const lvn_mesh_vertex    *vertices;    /* device pointers */
+    const lvn_mesh_triangle  *triangles;
+    const lvn_seam_node_info *seamNodes;
+    int64_t totalVertices, totalTriangles, totalSeamNodes, totalEdges;
+    int32_t nonEmptyChunks;
+} lvn_batch_device_view;
+int lvn_meshgen_generate_batch_device(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                      lvn_chunk_result *results, lvn_batch_device_view *view);
+
+/* applyCSGOperations over many chunks in one pass (same ops for every chunk) */
+int lvn_meshgen_apply_csg_operations_batch(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
+                                           int nChunks, const int32_t *chunkMinSize);
+
+/* ---- new: per-stage dump for parity tests -------------------------------- */
+
+typedef struct lvn_stage_dump {
+    /* capacities, set by the caller */
+    int32_t edgeCapacity, nodeCapacity;
+    /* counts, set by the callee */
+    int32_t numEdges, numNodes, numTriangles, numSeamNodes;
+    /* host buffers, any may be NULL */
+    uint8_t  *materials;     /* F^3, index x + F*y + F*F*z (shared_constants.cl:24-27) */
+    int32_t  *edgeKeys;      /* E: ((x | y<<s | z<<2s) << 2) | axis (density_field.cl:73) */
+    float    *edgeInfo;      /* 4E: normal.xyz, t (density_field.cl:150) */
+    uint32_t *nodeCodes;     /* N (octree.cl:34-47) */
+    int32_t  *nodeEdgeMasks; /* N (octree.cl:177-191) */
+    int32_t  *nodeMaterials; /* N: (dominant << 8) | cornerMask (octree.cl:199-200) */
+    float    *nodeQEFs;      /* 16N floats: QEFData (qef.cl:7-14) */
+    float    *nodePositions; /* 4N (octree.cl:327-330) */
+    float    *nodeNormals;   /* 4N (octree.cl:303-311) */
+} lvn_stage_dump;
+/* runs the path for one chunk with cold octree cache semantics and copies every stage out */
+int lvn_meshgen_debug_dump_chunk(lvn_meshgen *ctx, const int32_t min[3], int size, lvn_stage_dump *dump);
+
+/* ---- new: measurement hooks ---------------------------------------------- */
+
+enum {
+    LVN_STAGE_COLUMNS = 0,   /* S1 density: Terrain per column (noise.cl:205-223) */
+    LVN_STAGE_CLASSIFY,      /* S2+S4 edge scan, active voxels, prefix sums, compaction */
+    LVN_STAGE_HERMITE,       /* S3 FindEdgeIntersectionInfo (density_field.cl:96-151) */
+    LVN_STAGE_LEAVES,        /* S5+S6+S8+S9+S10 leaf QEF + solve + mesh + seams */
+    LVN_STAGE_FIELD,         /* u8 material field materialisation (CSG / 3-D density) */
+    LVN_STAGE_CSG,           /* a16 kernels */
+    LVN_STAGE_CUCKOO,        /* a9 kernels */
+    LVN_NUM_STAGES
+};
+typedef struct lvn_stage_stats {
+    double  ms[LVN_NUM_STAGES];         /* CUDA-event time on the context's stream, accumulated */
+    int64_t launches[LVN_NUM_STAGES];   /* kernel launches, accumulated */
+    int64_t terrainEvals;               /* Terrain() evaluations issued, accumulated */
+    int64_t edges, edgesY, nodes, triangles, seamNodes, chunks, nonEmptyChunks;
+} lvn_stage_stats;
+int lvn_meshgen_set_profiling(lvn_meshgen *ctx, int enabled);   /* per-stage events on/off */
+/* launch on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the context's own) */
+int lvn_meshgen_set_stream(lvn_meshgen *ctx, void *cudaStream);
+/* FP32 roofline denominator: independent FMA chains on every SM, CUDA-event timed (2 flop/FMA) */
+int lvn_measure_fp32_peak(double *tflops);
+int lvn_meshgen_get_stats(lvn_meshgen *ctx, lvn_stage_stats *out, int reset);
+
+/* ---- utilities of the path (a9, a15), usable on their own ---------------- */
+
+/* FindNextPrime, primes.h (primes.cpp:32-59) */
+int lvn_find_next_prime(int n);
+/* ExclusiveScan, compute.cpp:384-395: scan[i] = sum(data[0..i)); returns the total */
+int lvn_exclusive_scan(const int32_t *data, int32_t *scan, int count);
+/* CompactIndexArray, compute.cpp:424-442: stable; returns the compacted count */
+int lvn_compact_index_array(const int32_t *values, const int32_t *valid, int count, int32_t *out);
+/* RemoveDuplicates, compute.cpp:446-543: out = the distinct values (order unspecified, as in
+ * the reference); returns their count */
+int lvn_remove_duplicates(const int32_t *values, int count, int32_t *out);
+
+/* CuckooData + Cuckoo_InitialiseTable + Cuckoo_InsertKeys, compute_cuckoo.h:12-24; values are
+ * the key's index in the inserted array, as in cuckoo.cl:35 */
+typedef struct lvn_cuckoo lvn_cuckoo;
+lvn_cuckoo *lvn_cuckoo_create(unsigned int tableSize);
+int  lvn_cuckoo_insert_keys(lvn_cuckoo *table, const uint32_t *keys, unsigned int count);
+/* Cuckoo_Find, cuckoo.cl:73-104, for an array of keys; ~0u = not found */
+int  lvn_cuckoo_find(const lvn_cuckoo *table, const uint32_t *keys, unsigned int count, uint32_t *values);
+int  lvn_cuckoo_prime(const lvn_cuckoo *table);
+int  lvn_cuckoo_retries(const lvn_cuckoo *table);
+void lvn_cuckoo_destroy(lvn_cuckoo *table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEVEN_COMPUTE_H */

@@ -1,0 +1,439 @@
+"""Host-side mirror of the reference compute interface (leven/src/compute.h:12-81)
+over the C ABI of libleven_b200.so (include/leven_compute.h).
+
+Same names, argument meaning and error behaviour as the reference: every call
+returns an int, 0 = success, negative = failure (callers test ``< 0``,
+clipmap.cpp:379).  There is no CPU fallback: importing works without a GPU (so
+the symbol table can be checked), but every compute call fails with
+LVN_ERR_NO_DEVICE unless a CUDA device runs the sm_100a kernels.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libleven_b200.so")
+
+LVN_SUCCESS = 0
+LVN_CL_ERROR = -99999
+LVN_ERR_NO_DEVICE = -1
+LVN_ERR_OUT_OF_MEMORY = -4
+LVN_ERR_INVALID_VALUE = -30
+LVN_ERR_NOT_INITIALISED = -34
+LVN_ERR_CAPACITY = -61
+LVN_ERR_CUDA = -9999
+
+MATERIAL_NONE = 200      # volume_materials.h:7
+MATERIAL_AIR = 201       # volume_materials.h:8
+LEAF_SIZE_SCALE = 4      # volume_constants.h:7-8
+MAX_MESH_VERTICES = 14 * 1024          # render_types.h:62-68 (LEVEN defined)
+MAX_MESH_TRIANGLES = MAX_MESH_VERTICES * 2
+RenderShape_Cube, RenderShape_Sphere = 0, 1   # render_types.h:11-20
+
+LVN_STAGES = ("columns", "classify", "hermite", "leaves", "field", "csg", "cuckoo")
+
+# POD layouts (static_asserted against the C header in tests/test_abi.py)
+MeshVertex = np.dtype([("xyz", np.float32, 4), ("normal", np.float32, 4), ("colour", np.float32, 4)])
+MeshTriangle = np.dtype([("indices_", np.int32, 3)])
+SeamNodeInfo = np.dtype([("localspaceMin", np.int32, 4), ("position", np.float32, 4), ("normal", np.float32, 4)])
+ChunkResult = np.dtype([("numEdges", np.int32), ("numVertices", np.int32), ("numTriangles", np.int32),
+                        ("numSeamNodes", np.int32), ("vertexOffset", np.int32), ("triangleOffset", np.int32),
+                        ("seamOffset", np.int32), ("status", np.int32)])
+
+
+class CSGOperationInfo(C.Structure):
+    """compute.h:16-24"""
+    _fields_ = [("type", C.c_int32), ("brushShape", C.c_int32), ("material", C.c_int32),
+                ("rotateY", C.c_float), ("origin", C.c_float * 4), ("dimensions", C.c_float * 4)]
+
+    @classmethod
+    def make(cls, type_, shape, material, origin, dimensions, rotate_y=0.0):
+        op = cls()
+        op.type, op.brushShape, op.material, op.rotateY = int(type_), int(shape), int(material), float(rotate_y)
+        for i in range(3):
+            op.origin[i] = float(origin[i])
+            op.dimensions[i] = float(dimensions[i])
+        op.origin[3] = 0.0
+        op.dimensions[3] = 0.0
+        return op
+
+
+class AABB(C.Structure):
+    """aabb.h:95-96"""
+    _fields_ = [("min", C.c_int32 * 3), ("max", C.c_int32 * 3)]
+
+
+class BatchDeviceView(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("triangles", C.c_void_p), ("seamNodes", C.c_void_p),
+                ("totalVertices", C.c_int64), ("totalTriangles", C.c_int64), ("totalSeamNodes", C.c_int64),
+                ("totalEdges", C.c_int64), ("nonEmptyChunks", C.c_int32)]
+
+
+class StageDump(C.Structure):
+    _fields_ = [("edgeCapacity", C.c_int32), ("nodeCapacity", C.c_int32),
+                ("numEdges", C.c_int32), ("numNodes", C.c_int32), ("numTriangles", C.c_int32),
+                ("numSeamNodes", C.c_int32),
+                ("materials", C.c_void_p), ("edgeKeys", C.c_void_p), ("edgeInfo", C.c_void_p),
+                ("nodeCodes", C.c_void_p), ("nodeEdgeMasks", C.c_void_p), ("nodeMaterials", C.c_void_p),
+                ("nodeQEFs", C.c_void_p), ("nodePositions", C.c_void_p), ("nodeNormals", C.c_void_p)]
+
+
+class StageStats(C.Structure):
+    _fields_ = [("ms", C.c_double * len(LVN_STAGES)), ("launches", C.c_int64 * len(LVN_STAGES)),
+                ("terrainEvals", C.c_int64), ("edges", C.c_int64), ("edgesY", C.c_int64), ("nodes", C.c_int64),
+                ("triangles", C.c_int64), ("seamNodes", C.c_int64), ("chunks", C.c_int64),
+                ("nonEmptyChunks", C.c_int64)]
+
+
+# every symbol include/leven_compute.h declares: name -> (restype, argtypes)
+_P, _I, _U, _F, _I64 = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_int64
+ABI = {
+    "lvn_compute_set_device": (_I, [_I]),
+    "lvn_compute_initialise": (_I, [_I, _U, _I]),
+    "lvn_compute_shutdown": (_I, []),
+    "lvn_compute_set_noise_seed": (_I, [_I]),
+    "lvn_compute_set_noise_image": (_I, [_P]),
+    "lvn_compute_get_noise_image": (_I, [_P]),
+    "lvn_compute_set_density_function": (_I, [_I, _F]),
+    "lvn_compute_store_csg_operation": (_I, [_P, _P]),
+    "lvn_compute_clear_csg_operations": (_I, []),
+    "lvn_error_string": (C.c_char_p, [_I]),
+    "lvn_last_cuda_error": (C.c_char_p, []),
+    "lvn_meshgen_create": (_P, [_I]),
+    "lvn_meshgen_destroy": (None, [_P]),
+    "lvn_meshgen_voxels_per_chunk": (_I, [_P]),
+    "lvn_meshgen_apply_csg_operations": (_I, [_P, _P, _I, _P, _I]),
+    "lvn_meshgen_free_chunk_octree": (_I, [_P, _P, _I]),
+    "lvn_meshgen_is_chunk_empty": (_I, [_P, _P, _I, _P]),
+    "lvn_meshgen_generate_chunk_mesh": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _P]),
+    "lvn_meshgen_generate_batch": (_I, [_P, _I, _P, _P, _I64, _P, _I64, _P, _I64, _P]),
+    "lvn_meshgen_generate_batch_device": (_I, [_P, _I, _P, _P, _P]),
+    "lvn_meshgen_apply_csg_operations_batch": (_I, [_P, _P, _I, _I, _P]),
+    "lvn_meshgen_debug_dump_chunk": (_I, [_P, _P, _I, _P]),
+    "lvn_meshgen_set_profiling": (_I, [_P, _I]),
+    "lvn_meshgen_get_stats": (_I, [_P, _P, _I]),
+    "lvn_meshgen_set_stream": (_I, [_P, _P]),
+    "lvn_measure_fp32_peak": (_I, [_P]),
+    "lvn_find_next_prime": (_I, [_I]),
+    "lvn_exclusive_scan": (_I, [_P, _P, _I]),
+    "lvn_compact_index_array": (_I, [_P, _P, _I, _P]),
+    "lvn_remove_duplicates": (_I, [_P, _I, _P]),
+    "lvn_cuckoo_create": (_P, [_U]),
+    "lvn_cuckoo_insert_keys": (_I, [_P, _P, _U]),
+    "lvn_cuckoo_find": (_I, [_P, _P, _U, _P]),
+    "lvn_cuckoo_prime": (_I, [_P]),
+    "lvn_cuckoo_retries": (_I, [_P]),
+    "lvn_cuckoo_destroy": (None, [_P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libleven_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "leven_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i3(v):
+    return (C.c_int32 * 3)(int(v[0]), int(v[1]), int(v[2]))
+
+
+def GetCLErrorString(error):
+    """compute.h:81"""
+    return lib().lvn_error_string(int(error)).decode()
+
+
+def last_cuda_error():
+    return lib().lvn_last_cuda_error().decode()
+
+
+def Compute_SetDevice(device):
+    return lib().lvn_compute_set_device(int(device))
+
+
+def Compute_Initialise(noiseSeed, defaultMaterial, numCSGBrushes):
+    """compute.h:35"""
+    return lib().lvn_compute_initialise(int(noiseSeed), int(defaultMaterial), int(numCSGBrushes))
+
+
+def Compute_Shutdown():
+    """compute.h:36"""
+    return lib().lvn_compute_shutdown()
+
+
+def Compute_SetNoiseSeed(noiseSeed):
+    """compute.h:38"""
+    return lib().lvn_compute_set_noise_seed(int(noiseSeed))
+
+
+def Compute_SetNoiseImage(rgba):
+    rgba = np.ascontiguousarray(rgba, np.uint8).reshape(-1)
+    assert rgba.size == 256 * 256 * 4
+    return lib().lvn_compute_set_noise_image(_ptr(rgba))
+
+
+def Compute_GetNoiseImage():
+    out = np.zeros(256 * 256 * 4, np.uint8)
+    rc = lib().lvn_compute_get_noise_image(_ptr(out))
+    if rc < 0:
+        raise RuntimeError(GetCLErrorString(rc))
+    return out
+
+
+def Compute_SetDensityFunction(kind, param=0.5):
+    return lib().lvn_compute_set_density_function(int(kind), float(param))
+
+
+def Compute_StoreCSGOperation(opInfo, aabb_min, aabb_max):
+    """compute.h:39"""
+    bb = AABB()
+    for i in range(3):
+        bb.min[i] = int(aabb_min[i])
+        bb.max[i] = int(aabb_max[i])
+    return lib().lvn_compute_store_csg_operation(C.byref(opInfo), C.byref(bb))
+
+
+def Compute_ClearCSGOperations():
+    """compute.h:40"""
+    return lib().lvn_compute_clear_csg_operations()
+
+
+def CalcCSGOperationBounds(opInfo):
+    """clipmap.cpp:1638-1643 (CSG_OFFSET 0.5, CSG_BOUNDS_FUDGE 2, clipmap.cpp:1613-1614): the AABB
+    the caller passes to Compute_StoreCSGOperation."""
+    half = [int(np.float32(opInfo.dimensions[i]) * np.float32(LEAF_SIZE_SCALE)) + 2 for i in range(3)]
+    org = [int((np.float32(opInfo.origin[i]) - np.float32(0.5)) * np.float32(LEAF_SIZE_SCALE)) for i in range(3)]
+    return [org[i] - half[i] for i in range(3)], [org[i] + half[i] for i in range(3)]
+
+
+class MeshBuffer:
+    """render_types.h:70-90: fixed-capacity vertex / triangle arrays owned by the caller."""
+
+    def __init__(self, max_vertices=MAX_MESH_VERTICES, max_triangles=None):
+        self.vertices = np.zeros(max_vertices, MeshVertex)
+        self.triangles = np.zeros(max_triangles if max_triangles is not None else 2 * max_vertices, MeshTriangle)
+        self.numVertices = 0
+        self.numTriangles = 0
+
+
+class Compute_MeshGenContext:
+    """compute.h:46-77"""
+
+    def __init__(self, handle):
+        self.privateCtx_ = handle
+        self._L = lib()
+
+    @staticmethod
+    def create(voxelsPerChunk):
+        """compute.h:50; privateCtx_ may be None on failure, as in the reference (compute.cpp:605-610)."""
+        return Compute_MeshGenContext(lib().lvn_meshgen_create(int(voxelsPerChunk)))
+
+    def destroy(self):
+        if self.privateCtx_:
+            self._L.lvn_meshgen_destroy(self.privateCtx_)
+            self.privateCtx_ = None
+
+    def voxelsPerChunk(self):
+        return self._L.lvn_meshgen_voxels_per_chunk(self.privateCtx_)
+
+    def applyCSGOperations(self, opInfo, clipmapNodeMin, clipmapNodeSize):
+        arr = (CSGOperationInfo * len(opInfo))(*opInfo)
+        return self._L.lvn_meshgen_apply_csg_operations(self.privateCtx_, arr, len(opInfo), _i3(clipmapNodeMin),
+                                                        int(clipmapNodeSize))
+
+    def freeChunkOctree(self, min_, size):
+        return self._L.lvn_meshgen_free_chunk_octree(self.privateCtx_, _i3(min_), int(size))
+
+    def isChunkEmpty(self, min_, size):
+        """returns (error, isEmpty)"""
+        e = C.c_int(0)
+        rc = self._L.lvn_meshgen_is_chunk_empty(self.privateCtx_, _i3(min_), int(size), C.byref(e))
+        return rc, bool(e.value)
+
+    def generateChunkMesh(self, min_, clipmapNodeSize, meshBuffer, seamNodeBuffer):
+        """compute.h:68-72.  seamNodeBuffer is a python list that is cleared and refilled with one
+        SeamNodeInfo ndarray (the std::vector<SeamNodeInfo>& of the reference)."""
+        del seamNodeBuffer[:]
+        nV, nT, nS = C.c_int(0), C.c_int(0), C.c_int(0)
+        cap = 4096
+        while True:
+            seams = np.zeros(cap, SeamNodeInfo)
+            rc = self._L.lvn_meshgen_generate_chunk_mesh(
+                self.privateCtx_, _i3(min_), int(clipmapNodeSize),
+                _ptr(meshBuffer.vertices), len(meshBuffer.vertices), C.byref(nV),
+                _ptr(meshBuffer.triangles), len(meshBuffer.triangles), C.byref(nT),
+                _ptr(seams), cap, C.byref(nS))
+            if rc == LVN_ERR_CAPACITY and nS.value > cap:
+                cap = nS.value      # the vector grows; the MeshBuffer does not
+                continue
+            break
+        if rc < 0:
+            return rc
+        meshBuffer.numVertices, meshBuffer.numTriangles = nV.value, nT.value
+        seamNodeBuffer.append(seams[:nS.value].copy())
+        return rc
+
+    # ---- batch entry points (new) ---------------------------------------
+    def generateBatch(self, chunkMinSize, vertices, triangles, seamNodes):
+        """host arenas (numpy arrays of MeshVertex / MeshTriangle / SeamNodeInfo); returns (error, results)"""
+        ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
+        results = np.zeros(len(ms), ChunkResult)
+        rc = self._L.lvn_meshgen_generate_batch(self.privateCtx_, len(ms), _ptr(ms),
+                                                _ptr(vertices), len(vertices), _ptr(triangles), len(triangles),
+                                                _ptr(seamNodes), len(seamNodes), _ptr(results))
+        return rc, results
+
+    def generateBatchDevice(self, chunkMinSize):
+        """results stay in HBM; returns (error, results, view)"""
+        ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
+        results = np.zeros(len(ms), ChunkResult)
+        view = BatchDeviceView()
+        rc = self._L.lvn_meshgen_generate_batch_device(self.privateCtx_, len(ms), _ptr(ms), _ptr(results),
+                                                       C.byref(view))
+        return rc, results, view
+
+    def applyCSGOperationsBatch(self, opInfo, chunkMinSize):
+        ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
+        arr = (CSGOperationInfo * len(opInfo))(*opInfo)
+        return self._L.lvn_meshgen_apply_csg_operations_batch(self.privateCtx_, arr, len(opInfo), len(ms), _ptr(ms))
+
+    def debugDumpChunk(self, min_, size):
+        """every stage of one chunk as numpy arrays (parity tests)"""
+        V = self.voxelsPerChunk()
+        F = V + 2
+        ecap, ncap = 1 << 15, 1 << 15
+        while True:
+            d = StageDump()
+            d.edgeCapacity, d.nodeCapacity = ecap, ncap
+            bufs = dict(materials=np.zeros(F ** 3, np.uint8), edgeKeys=np.zeros(ecap, np.int32),
+                        edgeInfo=np.zeros((ecap, 4), np.float32), nodeCodes=np.zeros(ncap, np.uint32),
+                        nodeEdgeMasks=np.zeros(ncap, np.int32), nodeMaterials=np.zeros(ncap, np.int32),
+                        nodeQEFs=np.zeros((ncap, 16), np.float32), nodePositions=np.zeros((ncap, 4), np.float32),
+                        nodeNormals=np.zeros((ncap, 4), np.float32))
+            for k, v in bufs.items():
+                setattr(d, k, v.ctypes.data)
+            rc = self._L.lvn_meshgen_debug_dump_chunk(self.privateCtx_, _i3(min_), int(size), C.byref(d))
+            if rc == LVN_ERR_CAPACITY:
+                ecap, ncap = max(ecap, d.numEdges), max(ncap, d.numNodes)
+                continue
+            break
+        if rc < 0:
+            raise RuntimeError(f"debug_dump_chunk: {GetCLErrorString(rc)} {last_cuda_error()}")
+        E, N = d.numEdges, d.numNodes
+        out = dict(numEdges=E, numNodes=N, numTriangles=d.numTriangles, numSeamNodes=d.numSeamNodes,
+                   materials=bufs["materials"])
+        for k in ("edgeKeys", "edgeInfo"):
+            out[k] = bufs[k][:E].copy()
+        for k in ("nodeCodes", "nodeEdgeMasks", "nodeMaterials", "nodeQEFs", "nodePositions", "nodeNormals"):
+            out[k] = bufs[k][:N].copy()
+        return out
+
+    def setStream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None"""
+        return self._L.lvn_meshgen_set_stream(self.privateCtx_, C.c_void_p(cuda_stream))
+
+    def setProfiling(self, enabled):
+        return self._L.lvn_meshgen_set_profiling(self.privateCtx_, int(bool(enabled)))
+
+    def getStats(self, reset=False):
+        s = StageStats()
+        self._L.lvn_meshgen_get_stats(self.privateCtx_, C.byref(s), int(bool(reset)))
+        out = {f: getattr(s, f) for f in ("terrainEvals", "edges", "edgesY", "nodes", "triangles", "seamNodes",
+                                          "chunks", "nonEmptyChunks")}
+        out["ms"] = {n: s.ms[i] for i, n in enumerate(LVN_STAGES)}
+        out["launches"] = {n: s.launches[i] for i, n in enumerate(LVN_STAGES)}
+        return out
+
+
+def MeasureFP32Peak():
+    """measured non-tensor FP32 peak in TFLOP/s (roofline denominator of the FP32-bound stages)"""
+    v = C.c_double(0.0)
+    rc = lib().lvn_measure_fp32_peak(C.byref(v))
+    if rc < 0:
+        raise RuntimeError(GetCLErrorString(rc))
+    return v.value
+
+
+# ---- utilities of the path (compute.cpp:328-543, compute_cuckoo.h) -------------
+def FindNextPrime(n):
+    return lib().lvn_find_next_prime(int(n))
+
+
+def ExclusiveScan(data):
+    """returns (total, scan)"""
+    data = np.ascontiguousarray(data, np.int32)
+    scan = np.zeros_like(data)
+    total = lib().lvn_exclusive_scan(_ptr(data), _ptr(scan), len(data))
+    return total, scan
+
+
+def CompactIndexArray(values, valid):
+    values = np.ascontiguousarray(values, np.int32)
+    valid = np.ascontiguousarray(valid, np.int32)
+    out = np.zeros_like(values)
+    n = lib().lvn_compact_index_array(_ptr(values), _ptr(valid), len(values), _ptr(out))
+    if n < 0:
+        raise RuntimeError(GetCLErrorString(n))
+    return out[:n].copy()
+
+
+def RemoveDuplicates(values):
+    values = np.ascontiguousarray(values, np.int32)
+    out = np.zeros_like(values)
+    n = lib().lvn_remove_duplicates(_ptr(values), len(values), _ptr(out))
+    if n < 0:
+        raise RuntimeError(GetCLErrorString(n))
+    return out[:n].copy()
+
+
+class CuckooData:
+    """compute_cuckoo.h:12-24"""
+
+    def __init__(self):
+        self.h = None
+
+    def Cuckoo_InitialiseTable(self, tableSize):
+        self.h = lib().lvn_cuckoo_create(int(tableSize))
+        return LVN_SUCCESS if self.h else LVN_CL_ERROR
+
+    def Cuckoo_InsertKeys(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        return lib().lvn_cuckoo_insert_keys(self.h, _ptr(keys), len(keys))
+
+    def Cuckoo_Find(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        values = np.zeros_like(keys)
+        rc = lib().lvn_cuckoo_find(self.h, _ptr(keys), len(keys), _ptr(values))
+        if rc < 0:
+            raise RuntimeError(GetCLErrorString(rc))
+        return values
+
+    @property
+    def prime(self):
+        return lib().lvn_cuckoo_prime(self.h)
+
+    @property
+    def retries(self):
+        return lib().lvn_cuckoo_retries(self.h)
+
+    def destroy(self):
+        if self.h:
+            lib().lvn_cuckoo_destroy(self.h)
+            self.h = None

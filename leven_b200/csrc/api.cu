@@ -1,0 +1,1252 @@
+// Host side of libleven_b200.so: the C ABI of include/leven_compute.h.
+//
+// Replaces the reference's OpenCL host layer (paths relative to the reference tree):
+//   leven/src/compute.cpp               context, utilities, Compute_MeshGenContext
+//   leven/src/compute_density_field.cpp noise table, field cache, CSG op store / replay
+//   leven/src/compute_octree.cpp        octree cache, generateChunkMesh orchestration
+//   leven/src/compute_csg.cpp           ApplyCSGOperations
+//   leven/src/compute_cuckoo.cpp        table sizing, rehash loop
+//
+// One batch = four kernels and one host synchronisation (the reference: ~65 launches and ~10
+// blocking reads per chunk).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "lvn_internal.h"
+
+using namespace lvn;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static std::string g_lastCudaError;
+
+#define CU(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            char _b[512];                                                                    \
+            snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            g_lastCudaError = _b;                                                            \
+            return _e == cudaErrorMemoryAllocation ? LVN_ERR_OUT_OF_MEMORY : LVN_ERR_CUDA;   \
+        }                                                                                    \
+    } while (0)
+#define LV(call) do { int _r = (call); if (_r < 0) return _r; } while (0)
+
+extern "C" const char *lvn_last_cuda_error(void) { return g_lastCudaError.c_str(); }
+
+extern "C" const char *lvn_error_string(int error)
+{
+    switch (error) {
+    case LVN_SUCCESS: return "LVN_SUCCESS";
+    case LVN_CL_ERROR: return "LVN_CL_ERROR";
+    case LVN_ERR_NO_DEVICE: return "LVN_ERR_NO_DEVICE";
+    case LVN_ERR_OUT_OF_MEMORY: return "LVN_ERR_OUT_OF_MEMORY";
+    case LVN_ERR_INVALID_VALUE: return "LVN_ERR_INVALID_VALUE";
+    case LVN_ERR_NOT_INITIALISED: return "LVN_ERR_NOT_INITIALISED";
+    case LVN_ERR_CAPACITY: return "LVN_ERR_CAPACITY";
+    case LVN_ERR_CUDA: return "LVN_ERR_CUDA";
+    default: return "Unknown leven_b200 error code!";
+    }
+}
+
+// ---------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    int reserve(size_t n, bool keep = false)
+    {
+        if (n <= cap) return 0;
+        size_t want = std::max(n, cap + cap / 2);
+        T *np = nullptr;
+        CU(cudaMalloc((void **)&np, want * sizeof(T)));
+        if (keep && p && cap) CU(cudaMemcpy(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice));
+        if (p) cudaFree(p);
+        p = np;
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        CU(cudaMallocHost((void **)&p, n * sizeof(T)));
+        cap = n;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ---------------------------------------------------------------------------
+// process-wide state (ComputeContext, compute_local.h:17-24; g_storedOps, compute_density_field.cpp:23-24)
+// ---------------------------------------------------------------------------
+struct Global {
+    bool initialised = false;
+    int device = 0;
+    bool deviceChosen = false;
+    std::vector<uint8_t> image;
+    float2 *d_grad2 = nullptr;
+    float4 *d_grad3 = nullptr;
+    int defaultMaterial = 0;
+    int densityKind = 0;
+    float densityParam = 0.5f;
+    std::vector<lvn_csg_operation_info> storedOps;
+    std::vector<lvn_aabb> storedAABBs;
+    std::mt19937 cuckooRng;   // compute_cuckoo.cpp:46
+};
+static Global g;
+
+static DensityParams density_params()
+{
+    DensityParams dp;
+    dp.grad2 = g.d_grad2;
+    dp.grad3 = g.d_grad3;
+    dp.kind = g.densityKind;
+    dp.param = g.densityParam;
+    dp.defaultMaterial = g.defaultMaterial;
+    return dp;
+}
+
+extern "C" int lvn_compute_set_device(int cudaDevice)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return LVN_ERR_NO_DEVICE;
+    if (cudaDevice < 0 || cudaDevice >= count) return LVN_ERR_INVALID_VALUE;
+    g.device = cudaDevice;
+    g.deviceChosen = true;
+    CU(cudaSetDevice(cudaDevice));
+    return LVN_SUCCESS;
+}
+
+// ---- noise table (compute_density_field.cpp:28-125) -------------------------
+static const int kPerm256[256] = {151,160,137,91,90,15,
+  131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,
+  190, 6,148,247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,
+  88,237,149,56,87,174,20,125,136,171,168, 68,175,74,165,71,134,139,48,27,166,
+  77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,244,
+  102,143,54, 65,25,63,161, 1,216,80,73,209,76,132,187,208, 89,18,169,200,196,
+  135,130,116,188,159,86,164,100,109,198,173,186, 3,64,52,217,226,250,124,123,
+  5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,182,189,28,42,
+  223,183,170,213,119,248,152, 2,44,154,163, 70,221,153,101,155,167, 43,172,9,
+  129,22,39,253, 19,98,108,110,79,113,224,232,178,185, 112,104,218,246,97,228,
+  251,34,242,193,238,210,144,12,191,179,162,241, 81,51,145,235,249,14,239,107,
+  49,192,214, 31,181,199,106,157,184, 84,204,176,115,121,50,45,127, 4,150,254,
+  138,236,205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180};
+static const int kGrad3[16][3] = {{0,1,1},{0,1,-1},{0,-1,1},{0,-1,-1},{1,0,1},{1,0,-1},{-1,0,1},{-1,0,-1},
+    {1,1,0},{1,-1,0},{-1,1,0},{-1,-1,0},{1,0,-1},{-1,0,-1},{0,-1,1},{0,1,1}};
+
+static unsigned int noise_hash(int x, int y, int seed)   // NoiseHash, compute_density_field.cpp:69-88
+{
+    const unsigned int key = (((unsigned int)x << 24) | ((unsigned int)y << 16)) ^ (unsigned int)seed;
+    unsigned int hash = 0;
+    for (int i = 0; i < 4; i++) {
+        hash += (key >> (8 * i)) & 0xffu;
+        hash += (hash << 10);
+        hash ^= (hash >> 6);
+    }
+    hash += (hash << 3);
+    hash ^= (hash >> 11);
+    hash += (hash << 15);
+    return hash;
+}
+
+static void make_noise_image(int seed, std::vector<uint8_t> &rgba)
+{
+    // the reference initialiser holds 506 values: the table, then the table again from entry 6
+    // on; the last 6 of the 512 slots are zero (compute_density_field.cpp:28-53)
+    int perm[512];
+    for (int i = 0; i < 256; i++) perm[i] = kPerm256[i];
+    for (int i = 0; i < 250; i++) perm[256 + i] = kPerm256[6 + i];
+    for (int i = 506; i < 512; i++) perm[i] = 0;
+    // documented stand-in for std::shuffle(std::default_random_engine(seed)): Fisher-Yates from
+    // the top with std::mt19937(seed), j = next() % (i + 1)
+    std::mt19937 mt((unsigned int)seed);
+    for (int i = 511; i > 0; i--) std::swap(perm[i], perm[mt() % (unsigned int)(i + 1)]);
+    rgba.resize(256 * 256 * 4);
+    for (int i = 0; i < 256; i++)
+        for (int j = 0; j < 256; j++) {
+            const int offset = ((i * 256) + j) * 4;
+            const unsigned char value = (unsigned char)perm[noise_hash(i, j, seed) & 0x1ff];
+            rgba[offset + 0] = (uint8_t)(kGrad3[value & 0x0f][0] * 64 + 64);
+            rgba[offset + 1] = (uint8_t)(kGrad3[value & 0x0f][1] * 64 + 64);
+            rgba[offset + 2] = (uint8_t)(kGrad3[value & 0x0f][2] * 64 + 64);
+            rgba[offset + 3] = value;
+        }
+}
+
+static float int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
+
+// read_imagef(...).xyz * 4.f - 1.f for a UNORM8 texel (simplex.cl:124): byte/255 correctly rounded
+static float unorm_grad(uint8_t b)
+{
+    volatile float q = (float)b / 255.0f;
+    volatile float m = q * 4.f;
+    return m - 1.f;
+}
+
+static int upload_noise_image()
+{
+    std::vector<float2> g2(65536);
+    std::vector<float4> g3(65536);
+    for (int t = 0; t < 65536; t++) {
+        const uint8_t *px = &g.image[(size_t)t * 4];
+        g2[t] = make_float2(unorm_grad(px[0]), unorm_grad(px[1]));
+        // snoise3's second lookup uses the UNORM alpha v/255 as an un-centred x coordinate:
+        // NEAREST + REPEAT lands on column v, and on column 0 for v = 255 (simplex.cl:184-185)
+        const int col = px[3] == 255 ? 0 : (int)px[3];
+        g3[t] = make_float4(unorm_grad(px[0]), unorm_grad(px[1]), unorm_grad(px[2]), int_as_float_host(col));
+    }
+    if (!g.d_grad2) CU(cudaMalloc((void **)&g.d_grad2, 65536 * sizeof(float2)));
+    if (!g.d_grad3) CU(cudaMalloc((void **)&g.d_grad3, 65536 * sizeof(float4)));
+    CU(cudaMemcpy(g.d_grad2, g2.data(), 65536 * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g.d_grad3, g3.data(), 65536 * sizeof(float4), cudaMemcpyHostToDevice));
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_compute_set_noise_image(const uint8_t *rgba)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!rgba) return LVN_ERR_INVALID_VALUE;
+    g.image.assign(rgba, rgba + 256 * 256 * 4);
+    return upload_noise_image();
+}
+
+extern "C" int lvn_compute_get_noise_image(uint8_t *rgba)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    memcpy(rgba, g.image.data(), 256 * 256 * 4);
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_compute_set_noise_seed(int noiseSeed)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    make_noise_image(noiseSeed, g.image);
+    return upload_noise_image();
+}
+
+extern "C" int lvn_compute_initialise(int noiseSeed, unsigned int defaultMaterial, int numCSGBrushes)
+{
+    (void)numCSGBrushes;   // NUM_CSG_BRUSHES: the two brush shapes are compiled in (compute.cpp:222)
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        g_lastCudaError = "no CUDA device";
+        return LVN_ERR_NO_DEVICE;
+    }
+    if (defaultMaterial > 255u) return LVN_ERR_INVALID_VALUE;   // materials are stored as u8
+    if (g.deviceChosen) CU(cudaSetDevice(g.device));
+    else CU(cudaGetDevice(&g.device));
+    g.initialised = true;
+    g.defaultMaterial = (int)defaultMaterial;
+    g.cuckooRng = std::mt19937();
+    return lvn_compute_set_noise_seed(noiseSeed);
+}
+
+extern "C" int lvn_compute_shutdown(void)
+{
+    if (g.d_grad2) cudaFree(g.d_grad2);
+    if (g.d_grad3) cudaFree(g.d_grad3);
+    g.d_grad2 = nullptr;
+    g.d_grad3 = nullptr;
+    g.initialised = false;
+    g.storedOps.clear();
+    g.storedAABBs.clear();
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_compute_set_density_function(int kind, float param)
+{
+    if (kind != 0 && kind != 1) return LVN_ERR_INVALID_VALUE;
+    g.densityKind = kind;
+    g.densityParam = param;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_compute_store_csg_operation(const lvn_csg_operation_info *op, const lvn_aabb *aabb)
+{
+    if (!op || !aabb) return LVN_ERR_INVALID_VALUE;
+    g.storedOps.push_back(*op);
+    g.storedAABBs.push_back(*aabb);
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_compute_clear_csg_operations(void)
+{
+    g.storedOps.clear();
+    g.storedAABBs.clear();
+    return LVN_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// mesh generation context (MeshGenerationContext, compute_local.h:57-72)
+// ---------------------------------------------------------------------------
+struct Key {
+    int x, y, z, s;
+    bool operator==(const Key &o) const { return x == o.x && y == o.y && z == o.z && s == o.s; }
+};
+struct KeyHash {
+    size_t operator()(const Key &k) const
+    {
+        size_t h = 1469598103934665603ull;
+        for (int v : {k.x, k.y, k.z, k.s}) { h ^= (size_t)(unsigned int)v; h *= 1099511628211ull; }
+        return h;
+    }
+};
+
+// GPUDensityField (compute_local.h:28-38) for fields that must persist: CSG-edited ones and
+// those created by isChunkEmpty.  The cuckoo table maps edge key -> slot (compute_octree.cpp:107-109).
+struct FieldEntry {
+    int lastCSGOperation = 0;
+    int numEdges = 0;
+    uint8_t *d_field = nullptr;
+    int *d_keys = nullptr;
+    float4 *d_info = nullptr;
+    unsigned long long *d_table = nullptr;
+    unsigned int prime = 0;
+    unsigned int params[8] = {0};
+    int cuckooRetries = 0;
+    void release()
+    {
+        if (d_field) cudaFree(d_field);
+        if (d_keys) cudaFree(d_keys);
+        if (d_info) cudaFree(d_info);
+        if (d_table) cudaFree(d_table);
+        d_field = nullptr; d_keys = nullptr; d_info = nullptr; d_table = nullptr;
+    }
+};
+
+// GPUOctree (compute_local.h:44-50) reduced to what a later generateChunkMesh returns
+struct OctreeEntry {
+    int numNodes = 0, numQuads = 0, numSeams = 0;
+    lvn_mesh_vertex *d_v = nullptr;
+    int *d_t = nullptr;
+    lvn_seam_node_info *d_s = nullptr;
+    void release()
+    {
+        if (d_v) cudaFree(d_v);
+        if (d_t) cudaFree(d_t);
+        if (d_s) cudaFree(d_s);
+        d_v = nullptr; d_t = nullptr; d_s = nullptr;
+    }
+};
+
+struct lvn_meshgen {
+    Dims dims;
+    cudaStream_t stream = nullptr;      // where the kernels go (own stream or the caller's)
+    cudaStream_t ownStream = nullptr;
+    std::unordered_map<Key, FieldEntry, KeyHash> fields;
+    std::unordered_map<Key, OctreeEntry, KeyHash> octrees;
+
+    // batch workspace
+    DevBuf<ChunkDesc> d_descs;
+    DevBuf<ChunkHdr> d_hdrs;
+    DevBuf<int4> d_colOrigins;
+    DevBuf<float> d_heights;
+    DevBuf<unsigned long long> d_bitsLo;
+    DevBuf<unsigned int> d_bitsHi, d_rowE, d_rowN, d_rowQ, d_rowS;
+    DevBuf<int> d_edgeKeys;
+    DevBuf<float4> d_edgeInfo;
+    DevBuf<lvn_mesh_vertex> d_vertices;
+    DevBuf<int> d_tris;
+    DevBuf<lvn_seam_node_info> d_seams;
+    DevBuf<ArenaCounters> d_counters;
+    DevBuf<uint8_t> d_tmpFields;
+    DevBuf<uint8_t *> d_fieldPtrs;
+    // debug stage outputs
+    DevBuf<unsigned int> d_dbgCodes;
+    DevBuf<int> d_dbgMasks, d_dbgMats;
+    DevBuf<float> d_dbgQefs;
+    DevBuf<float4> d_dbgPos, d_dbgNrm;
+    // csg scratch
+    DevBuf<unsigned int> d_touched, d_csgCounts;
+    DevBuf<CsgOpDev> d_ops;
+
+    PinBuf<ChunkDesc> h_descs;
+    PinBuf<ChunkHdr> h_hdrs;
+    PinBuf<int4> h_colOrigins;
+    PinBuf<ArenaCounters> h_counters;
+    PinBuf<unsigned int> h_small;
+
+    ArenaCounters lastCounters = {};
+    int lastN = 0;
+
+    bool profiling = false;
+    cudaEvent_t ev[2 * LVN_NUM_STAGES] = {nullptr};
+    bool evUsed[LVN_NUM_STAGES] = {false};
+    lvn_stage_stats stats = {};
+};
+
+static Key make_key(const int32_t min[3], int size) { return Key{min[0], min[1], min[2], size}; }
+
+extern "C" lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk)
+{
+    if (!g.initialised) return nullptr;
+    // power of two, 8..64: one sign row must fit 96 bits
+    if (voxelsPerChunk < 8 || voxelsPerChunk > 64 || (voxelsPerChunk & (voxelsPerChunk - 1))) return nullptr;
+    lvn_meshgen *ctx = new lvn_meshgen;
+    int l = 0;
+    while ((1 << (l + 1)) <= voxelsPerChunk) l++;
+    ctx->dims.V = voxelsPerChunk;
+    ctx->dims.H = voxelsPerChunk + 1;
+    ctx->dims.F = voxelsPerChunk + 2;
+    ctx->dims.depth = l;            // MAX_OCTREE_DEPTH, compute.cpp:271
+    ctx->dims.shift = l + 1;        // compute.cpp:251
+    ctx->dims.mask = (1 << (l + 1)) - 1;
+    if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    ctx->stream = ctx->ownStream;
+    for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+    return ctx;
+}
+
+extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
+{
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->fields) kv.second.release();
+    for (auto &kv : ctx->octrees) kv.second.release();
+    ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_colOrigins.release(); ctx->d_heights.release();
+    ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
+    ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release();
+    ctx->d_vertices.release(); ctx->d_tris.release(); ctx->d_seams.release(); ctx->d_counters.release();
+    ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
+    ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
+    ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
+    ctx->d_ops.release();
+    ctx->h_descs.release(); ctx->h_hdrs.release(); ctx->h_colOrigins.release(); ctx->h_counters.release();
+    ctx->h_small.release();
+    for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+}
+
+extern "C" int lvn_meshgen_voxels_per_chunk(const lvn_meshgen *ctx) { return ctx ? ctx->dims.V : 0; }
+
+extern "C" int lvn_meshgen_set_profiling(lvn_meshgen *ctx, int enabled)
+{
+    if (!ctx) return LVN_ERR_INVALID_VALUE;
+    ctx->profiling = enabled != 0;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_set_stream(lvn_meshgen *ctx, void *cudaStream)
+{
+    if (!ctx) return LVN_ERR_INVALID_VALUE;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cudaStream ? (cudaStream_t)cudaStream : ctx->ownStream;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_measure_fp32_peak(double *tflops)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!tflops) return LVN_ERR_INVALID_VALUE;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, g.device));
+    float *sink = nullptr;
+    CU(cudaMalloc((void **)&sink, 4));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(e0, 0));
+        launch_fma_peak(sink, iters, blocks, 0);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_get_stats(lvn_meshgen *ctx, lvn_stage_stats *out, int reset)
+{
+    if (!ctx || !out) return LVN_ERR_INVALID_VALUE;
+    *out = ctx->stats;
+    if (reset) memset(&ctx->stats, 0, sizeof(ctx->stats));
+    return LVN_SUCCESS;
+}
+
+struct StageTimer {   // CUDA events around one stage on the context's stream
+    lvn_meshgen *ctx;
+    int stage;
+    StageTimer(lvn_meshgen *c, int s, int launches) : ctx(c), stage(s)
+    {
+        ctx->stats.launches[stage] += launches;
+        if (ctx->profiling) cudaEventRecord(ctx->ev[2 * stage], ctx->stream);
+    }
+    ~StageTimer()
+    {
+        if (ctx->profiling) { cudaEventRecord(ctx->ev[2 * stage + 1], ctx->stream); ctx->evUsed[stage] = true; }
+    }
+};
+
+static void collect_stage_times(lvn_meshgen *ctx)   // call after the stream is synchronised
+{
+    if (!ctx->profiling) return;
+    for (int s = 0; s < LVN_NUM_STAGES; s++) {
+        if (!ctx->evUsed[s]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[2 * s], ctx->ev[2 * s + 1]) == cudaSuccess) ctx->stats.ms[s] += ms;
+        ctx->evUsed[s] = false;
+    }
+}
+
+// ColourForMinLeafSize(clipmapNodeSize / CLIPMAP_LEAF_SIZE), clipmap.cpp:329-352, compute_octree.cpp:252
+static void colour_for_size(int size, float rgb[3])
+{
+    switch (size / (LVN_LEAF_SIZE_SCALE * 64)) {
+    case 1:  rgb[0] = 0.3f; rgb[1] = 0.1f; rgb[2] = 0.f;  break;
+    case 2:  rgb[0] = 0.f;  rgb[1] = 0.f;  rgb[2] = 0.5f; break;
+    case 4:  rgb[0] = 0.f;  rgb[1] = 0.5f; rgb[2] = 0.5f; break;
+    case 8:  rgb[0] = 0.5f; rgb[1] = 0.f;  rgb[2] = 0.5f; break;
+    case 16: rgb[0] = 0.f;  rgb[1] = 0.5f; rgb[2] = 0.f;  break;
+    default: rgb[0] = 0.5f; rgb[1] = 0.f;  rgb[2] = 0.f;  break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one pass of the path over n chunks; results stay in the context's arenas
+// ---------------------------------------------------------------------------
+struct BatchOpts {
+    bool debug = false;          // fill the per-node stage dumps
+    bool ignoreFieldCache = false;
+};
+
+static int fill_desc(lvn_meshgen *ctx, const int32_t *ms, ChunkDesc &cd)
+{
+    const Dims &d = ctx->dims;
+    const int size = ms[3];
+    if (size <= 0 || size % (d.V * LVN_LEAF_SIZE_SCALE) != 0) return LVN_ERR_INVALID_VALUE;
+    memset(&cd, 0, sizeof(cd));
+    cd.scale = size / (d.V * LVN_LEAF_SIZE_SCALE);
+    cd.ox = ms[0] / LVN_LEAF_SIZE_SCALE;   // LeafScaleVec: C++ integer division
+    cd.oy = ms[1] / LVN_LEAF_SIZE_SCALE;
+    cd.oz = ms[2] / LVN_LEAF_SIZE_SCALE;
+    cd.minx = ms[0]; cd.miny = ms[1]; cd.minz = ms[2];
+    cd.size = size;
+    colour_for_size(size, cd.colour);
+    return LVN_SUCCESS;
+}
+
+static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const BatchOpts &opts)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!ctx || n < 0 || (n > 0 && !chunkMinSize)) return LVN_ERR_INVALID_VALUE;
+    const Dims &d = ctx->dims;
+    const size_t FF = (size_t)d.F * d.F, HH = (size_t)d.H * d.H, VV = (size_t)d.V * d.V, F3 = FF * d.F;
+    cudaStream_t st = ctx->stream;
+    ctx->lastN = n;
+    memset(&ctx->lastCounters, 0, sizeof(ctx->lastCounters));
+    if (n == 0) return LVN_SUCCESS;
+
+    // ---- descriptors, column-set dedupe, cached fields ----
+    LV(ctx->h_descs.reserve(n));
+    LV(ctx->h_colOrigins.reserve(n));
+    LV(ctx->h_hdrs.reserve(n));
+    LV(ctx->h_counters.reserve(1));
+    std::map<std::tuple<int, int, int>, int> colSets;
+    int numColSets = 0, numTmpFields = 0;
+    std::vector<int> tmpFieldChunk;
+    for (int i = 0; i < n; i++) {
+        ChunkDesc &cd = ctx->h_descs.p[i];
+        LV(fill_desc(ctx, &chunkMinSize[4 * i], cd));
+        auto it = opts.ignoreFieldCache ? ctx->fields.end() : ctx->fields.find(make_key(&chunkMinSize[4 * i], cd.size));
+        if (it != ctx->fields.end()) {
+            const FieldEntry &fe = it->second;
+            cd.source = SRC_FIELD;
+            cd.edgeMode = EDGES_CACHED;
+            cd.field = fe.d_field;
+            cd.cachedNumEdges = fe.numEdges;
+            cd.cachedKeys = fe.d_keys;
+            cd.cachedInfo = fe.d_info;
+            cd.cuckooTable = fe.d_table;
+            cd.cuckooPrime = fe.prime;
+            memcpy(cd.cuckooParams, fe.params, sizeof(fe.params));
+        } else if (g.densityKind == 0) {
+            cd.source = SRC_HEIGHTS;
+            cd.edgeMode = EDGES_FRESH;
+            auto key = std::make_tuple(cd.ox, cd.oz, cd.scale);
+            auto cs = colSets.find(key);
+            if (cs == colSets.end()) {
+                ctx->h_colOrigins.p[numColSets] = make_int4(cd.ox, cd.oz, cd.scale, 0);
+                cs = colSets.emplace(key, numColSets++).first;
+            }
+            cd.colSet = cs->second;
+        } else {
+            cd.source = SRC_FIELD;
+            cd.edgeMode = EDGES_FRESH;
+            tmpFieldChunk.push_back(i);
+            numTmpFields++;
+        }
+    }
+
+    // ---- workspace ----
+    LV(ctx->d_descs.reserve(n));
+    LV(ctx->d_hdrs.reserve(n));
+    LV(ctx->d_colOrigins.reserve(std::max(numColSets, 1)));
+    LV(ctx->d_heights.reserve(std::max<size_t>((size_t)numColSets * FF, 1)));
+    LV(ctx->d_bitsLo.reserve(n * FF));
+    LV(ctx->d_bitsHi.reserve(n * FF));
+    LV(ctx->d_rowE.reserve(n * HH));
+    LV(ctx->d_rowN.reserve(n * VV));
+    LV(ctx->d_rowQ.reserve(n * VV));
+    LV(ctx->d_rowS.reserve(n * VV));
+    LV(ctx->d_counters.reserve(1));
+    if (numTmpFields) {
+        LV(ctx->d_tmpFields.reserve((size_t)numTmpFields * F3));
+        for (int k = 0; k < numTmpFields; k++)
+            ctx->h_descs.p[tmpFieldChunk[k]].field = ctx->d_tmpFields.p + (size_t)k * F3;
+    }
+    // first-guess arena sizes; a batch that needs more reports it in the counters and is re-run
+    LV(ctx->d_edgeKeys.reserve(std::max<size_t>((size_t)n * 2048, 1u << 16)));
+    LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
+    LV(ctx->d_vertices.reserve(std::max<size_t>((size_t)n * 2048, 1u << 16)));
+    LV(ctx->d_tris.reserve(ctx->d_vertices.cap * 6 * 2));
+    LV(ctx->d_seams.reserve(std::max<size_t>((size_t)n * 512, 1u << 14)));
+
+    CU(cudaMemcpyAsync(ctx->d_descs.p, ctx->h_descs.p, n * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
+    if (numColSets)
+        CU(cudaMemcpyAsync(ctx->d_colOrigins.p, ctx->h_colOrigins.p, numColSets * sizeof(int4), cudaMemcpyHostToDevice, st));
+
+    const DensityParams dp = density_params();
+    ChunkScratch ws;
+    ws.bitsLo = ctx->d_bitsLo.p; ws.bitsHi = ctx->d_bitsHi.p;
+    ws.rowE = ctx->d_rowE.p; ws.rowN = ctx->d_rowN.p; ws.rowQ = ctx->d_rowQ.p; ws.rowS = ctx->d_rowS.p;
+
+    if (numColSets) {
+        StageTimer t(ctx, LVN_STAGE_COLUMNS, 1);
+        launch_columns(dp, d, ctx->d_colOrigins.p, numColSets, ctx->d_heights.p, st);
+        ctx->stats.terrainEvals += (int64_t)numColSets * (int64_t)FF;
+    }
+    if (numTmpFields) {
+        // 3-D density: materialise the u8 field (descs of the other chunks are skipped by pointer)
+        StageTimer t(ctx, LVN_STAGE_FIELD, 1);
+        std::vector<ChunkDesc> sub(numTmpFields);
+        std::vector<uint8_t *> subPtrs(numTmpFields);
+        for (int k = 0; k < numTmpFields; k++) { sub[k] = ctx->h_descs.p[tmpFieldChunk[k]]; subPtrs[k] = (uint8_t *)sub[k].field; }
+        // reuse the tail of d_descs / d_fieldPtrs: upload compact arrays
+        DevBuf<ChunkDesc> dsub; DevBuf<uint8_t *> dptr;
+        LV(dsub.reserve(numTmpFields)); LV(dptr.reserve(numTmpFields));
+        CU(cudaMemcpyAsync(dsub.p, sub.data(), numTmpFields * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dptr.p, subPtrs.data(), numTmpFields * sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
+        launch_field_density(dp, d, dsub.p, numTmpFields, dptr.p, st);
+        CU(cudaStreamSynchronize(st));
+        dsub.release(); dptr.release();
+    }
+
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (opts.debug) {
+            LV(ctx->d_dbgCodes.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgMasks.reserve(ctx->d_vertices.cap));
+            LV(ctx->d_dbgMats.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgQefs.reserve(ctx->d_vertices.cap * 16));
+            LV(ctx->d_dbgPos.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgNrm.reserve(ctx->d_vertices.cap));
+        }
+        ArenaCaps caps;
+        caps.edges = (unsigned int)std::min<size_t>(ctx->d_edgeKeys.cap, 0xffffffffu);
+        caps.nodes = (unsigned int)std::min<size_t>(ctx->d_vertices.cap, 0xffffffffu);
+        caps.quads = (unsigned int)std::min<size_t>(ctx->d_tris.cap / 6, 0xffffffffu);
+        caps.seams = (unsigned int)std::min<size_t>(ctx->d_seams.cap, 0xffffffffu);
+        CU(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ArenaCounters), st));
+        {
+            StageTimer t(ctx, LVN_STAGE_CLASSIFY, 1);
+            launch_classify(d, ctx->d_descs.p, n, ctx->d_heights.p, ctx->d_hdrs.p, ws, ctx->d_counters.p, caps,
+                            ctx->d_edgeKeys.p, st);
+        }
+        {
+            StageTimer t(ctx, LVN_STAGE_HERMITE, 1);
+            launch_hermite(dp, d, ctx->d_descs.p, n, ctx->d_hdrs.p, ctx->d_heights.p, ctx->d_edgeKeys.p,
+                           ctx->d_edgeInfo.p, st);
+        }
+        {
+            StageTimer t(ctx, LVN_STAGE_LEAVES, 1);
+            NodeDebug dbg = {};
+            if (opts.debug) {
+                dbg.codes = ctx->d_dbgCodes.p; dbg.edgeMasks = ctx->d_dbgMasks.p; dbg.matWords = ctx->d_dbgMats.p;
+                dbg.qefs = ctx->d_dbgQefs.p; dbg.positions = ctx->d_dbgPos.p; dbg.normals = ctx->d_dbgNrm.p;
+            }
+            launch_leaves(dp, d, ctx->d_descs.p, n, ctx->d_hdrs.p, ws, ctx->d_edgeInfo.p, ctx->d_vertices.p,
+                          ctx->d_tris.p, ctx->d_seams.p, dbg, st);
+        }
+        CU(cudaMemcpyAsync(ctx->h_hdrs.p, ctx->d_hdrs.p, n * sizeof(ChunkHdr), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, sizeof(ArenaCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        collect_stage_times(ctx);
+        const ArenaCounters &c = *ctx->h_counters.p;
+        if (!c.overflow) {
+            ctx->lastCounters = c;
+            int64_t ey = 0;
+            for (int i = 0; i < n; i++) ey += ctx->h_hdrs.p[i].Ey;
+            ctx->stats.edges += c.edges; ctx->stats.edgesY += ey; ctx->stats.nodes += c.nodes;
+            ctx->stats.triangles += 2 * (int64_t)c.quads; ctx->stats.seamNodes += c.seams;
+            ctx->stats.chunks += n; ctx->stats.nonEmptyChunks += c.nonEmpty;
+            if (g.densityKind == 0) ctx->stats.terrainEvals += 4 * ey + 19 * ((int64_t)c.edges - ey);
+            return LVN_SUCCESS;
+        }
+        // grow to what this batch asked for (+12%) and run again
+        LV(ctx->d_edgeKeys.reserve((size_t)c.edges + c.edges / 8 + 1024));
+        LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
+        LV(ctx->d_vertices.reserve((size_t)c.nodes + c.nodes / 8 + 1024));
+        LV(ctx->d_tris.reserve(((size_t)c.quads + c.quads / 8 + 1024) * 6));
+        LV(ctx->d_seams.reserve((size_t)c.seams + c.seams / 8 + 1024));
+    }
+    return LVN_ERR_CAPACITY;
+}
+
+static void fill_results(lvn_meshgen *ctx, int n, lvn_chunk_result *results)
+{
+    for (int i = 0; i < n; i++) {
+        const ChunkHdr &h = ctx->h_hdrs.p[i];
+        lvn_chunk_result &r = results[i];
+        r.numEdges = h.E;
+        // a chunk whose octree yields no quad exports an empty mesh buffer, but still its seam
+        // nodes (GenerateMeshFromOctree returns before filling the buffer, compute_octree.cpp:227-232)
+        r.numVertices = h.Q > 0 ? h.N : 0;
+        r.numTriangles = 2 * h.Q;
+        r.numSeamNodes = h.S;
+        r.vertexOffset = h.nodeBase;
+        r.triangleOffset = 2 * h.quadBase;
+        r.seamOffset = h.seamBase;
+        r.status = h.status;
+    }
+}
+
+extern "C" int lvn_meshgen_generate_batch_device(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                                 lvn_chunk_result *results, lvn_batch_device_view *view)
+{
+    BatchOpts opts;
+    LV(run_batch(ctx, nChunks, chunkMinSize, opts));
+    if (results) fill_results(ctx, nChunks, results);
+    if (view) {
+        view->vertices = ctx->d_vertices.p;
+        view->triangles = (const lvn_mesh_triangle *)ctx->d_tris.p;
+        view->seamNodes = ctx->d_seams.p;
+        view->totalVertices = ctx->lastCounters.nodes;
+        view->totalTriangles = 2 * (int64_t)ctx->lastCounters.quads;
+        view->totalSeamNodes = ctx->lastCounters.seams;
+        view->totalEdges = ctx->lastCounters.edges;
+        view->nonEmptyChunks = (int32_t)ctx->lastCounters.nonEmpty;
+    }
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                          lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                          lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                          lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                          lvn_chunk_result *results)
+{
+    if (!results) return LVN_ERR_INVALID_VALUE;
+    BatchOpts opts;
+    LV(run_batch(ctx, nChunks, chunkMinSize, opts));
+    fill_results(ctx, nChunks, results);
+    const ArenaCounters &c = ctx->lastCounters;
+    if ((int64_t)c.nodes > vertexCapacity || 2 * (int64_t)c.quads > triangleCapacity || (int64_t)c.seams > seamCapacity)
+        return LVN_ERR_CAPACITY;
+    cudaStream_t st = ctx->stream;
+    if (c.nodes) CU(cudaMemcpyAsync(vertices, ctx->d_vertices.p, (size_t)c.nodes * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToHost, st));
+    if (c.quads) CU(cudaMemcpyAsync(triangles, ctx->d_tris.p, (size_t)c.quads * 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (c.seams) CU(cudaMemcpyAsync(seamNodes, ctx->d_seams.p, (size_t)c.seams * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return LVN_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// cuckoo table of a field entry (compute_cuckoo.cpp:49-138)
+// ---------------------------------------------------------------------------
+static void draw_cuckoo_params(unsigned int *params8)
+{
+    std::uniform_int_distribution<uint32_t> distribution(1u << 15, 1u << 30);   // compute_cuckoo.cpp:47
+    for (int i = 0; i < 8; i++) params8[i] = distribution(g.cuckooRng);
+}
+
+static int build_cuckoo(lvn_meshgen *ctx, const unsigned int *d_keys, unsigned int count,
+                        unsigned long long **d_table, unsigned int *prime, unsigned int *params8, int *retries)
+{
+    cudaStream_t st = ctx->stream;
+    StageTimer t(ctx, LVN_STAGE_CUCKOO, 0);
+    const unsigned int want = std::max(2048u, count * 2u);   // MIN_TABLE_SIZE
+    *prime = (unsigned int)host_find_next_prime((int)want);
+    if (*d_table) { cudaFree(*d_table); *d_table = nullptr; }
+    CU(cudaMalloc((void **)d_table, (size_t)*prime * sizeof(unsigned long long)));
+    LV(ctx->d_csgCounts.reserve(8));
+    LV(ctx->h_small.reserve(8));
+    for (int attempt = 0; attempt < 64; attempt++) {
+        draw_cuckoo_params(params8);
+        launch_fill_u64(*d_table, *prime, ~0ull, st);
+        CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, sizeof(unsigned int), st));
+        launch_cuckoo_insert(d_keys, count, *d_table, *prime, params8, ctx->d_csgCounts.p, st);
+        ctx->stats.launches[LVN_STAGE_CUCKOO] += 2;
+        CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ctx->h_small.p[0] == 0) { if (retries) *retries = attempt; return LVN_SUCCESS; }
+    }
+    return LVN_CL_ERROR;
+}
+
+// ---------------------------------------------------------------------------
+// density-field cache (LoadDensityField / StoreDensityField, compute_density_field.cpp:235-308)
+// ---------------------------------------------------------------------------
+
+// GenerateDefaultDensityField + FindDefaultEdges into a persistent entry
+static int materialise_default_field(lvn_meshgen *ctx, const int32_t min[3], int size, FieldEntry &fe)
+{
+    const Dims &d = ctx->dims;
+    const size_t F3 = (size_t)d.F * d.F * d.F;
+    int32_t ms[4] = {min[0], min[1], min[2], size};
+    BatchOpts opts;
+    opts.ignoreFieldCache = true;
+    LV(run_batch(ctx, 1, ms, opts));
+    cudaStream_t st = ctx->stream;
+    const ChunkHdr &h = ctx->h_hdrs.p[0];
+    CU(cudaMalloc((void **)&fe.d_field, F3));
+    if (g.densityKind == 0) {
+        StageTimer t(ctx, LVN_STAGE_FIELD, 1);
+        LV(ctx->d_fieldPtrs.reserve(1));
+        CU(cudaMemcpyAsync(ctx->d_fieldPtrs.p, &fe.d_field, sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
+        launch_field_from_heights(d, ctx->d_descs.p, 1, ctx->d_heights.p, g.defaultMaterial, ctx->d_fieldPtrs.p, st);
+    } else {
+        CU(cudaMemcpyAsync(fe.d_field, ctx->d_tmpFields.p, F3, cudaMemcpyDeviceToDevice, st));
+    }
+    fe.numEdges = h.E;
+    fe.lastCSGOperation = 0;
+    if (h.E > 0) {
+        CU(cudaMalloc((void **)&fe.d_keys, (size_t)h.E * sizeof(int)));
+        CU(cudaMalloc((void **)&fe.d_info, (size_t)h.E * sizeof(float4)));
+        CU(cudaMemcpyAsync(fe.d_keys, ctx->d_edgeKeys.p + h.edgeBase, (size_t)h.E * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fe.d_info, ctx->d_edgeInfo.p + h.edgeBase, (size_t)h.E * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    if (h.E > 0)
+        LV(build_cuckoo(ctx, (const unsigned int *)fe.d_keys, (unsigned int)h.E, &fe.d_table, &fe.prime, fe.params, &fe.cuckooRetries));
+    return LVN_SUCCESS;
+}
+
+// ApplyCSGOperations, compute_csg.cpp:11-220
+static int apply_csg_to_field(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
+                              const int32_t min[3], int size, FieldEntry &fe)
+{
+    if (numOps <= 0) return LVN_SUCCESS;
+    const Dims &d = ctx->dims;
+    cudaStream_t st = ctx->stream;
+    int32_t ms[4] = {min[0], min[1], min[2], size};
+    ChunkDesc cd;
+    LV(fill_desc(ctx, ms, cd));
+
+    std::vector<CsgOpDev> hops(numOps);
+    for (int i = 0; i < numOps; i++) {
+        const lvn_csg_operation_info &o = ops[i];
+        if (o.material < 0 || o.material > 255 || (o.brushShape != 0 && o.brushShape != 1) || (o.type != 0 && o.type != 1))
+            return LVN_ERR_INVALID_VALUE;
+        CsgOpDev &v = hops[i];
+        v.type = o.type; v.shape = o.brushShape; v.material = o.material; v.pad = 0;
+        v.ox = o.origin[0]; v.oy = o.origin[1]; v.oz = o.origin[2];
+        v.dx = o.dimensions[0]; v.dy = o.dimensions[1]; v.dz = o.dimensions[2];
+        v.c = cosf(o.rotateY);   // pR(), hg_sdf.glsl:460-463; host libm so that every
+        v.s = sinf(o.rotateY);   // implementation fed the same op sees the same rotation
+    }
+    const size_t numWords = ((size_t)3 * d.H * d.H * d.H + 31) / 32;
+    LV(ctx->d_ops.reserve(numOps));
+    LV(ctx->d_touched.reserve(numWords));
+    LV(ctx->d_csgCounts.reserve(8));
+    LV(ctx->h_small.reserve(8));
+    CU(cudaMemcpyAsync(ctx->d_ops.p, hops.data(), numOps * sizeof(CsgOpDev), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_touched.p, 0, numWords * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, 8 * sizeof(unsigned int), st));
+    {
+        StageTimer t(ctx, LVN_STAGE_CSG, 2);
+        launch_csg_materials(d, cd, ctx->d_ops.p, numOps, fe.d_field, ctx->d_touched.p, ctx->d_csgCounts.p + 2, st);
+        launch_csg_count(d, fe.d_field, ctx->d_touched.p, fe.d_keys, fe.numEdges, ctx->d_csgCounts.p, st);
+    }
+    CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));   // hops must outlive the copy as well
+    collect_stage_times(ctx);
+    const unsigned int kept = ctx->h_small.p[0], created = ctx->h_small.p[1], changed = ctx->h_small.p[2];
+    if (changed == 0) return LVN_SUCCESS;   // numUpdatedPoints <= 0, compute_csg.cpp:62-66
+
+    // When every old edge is invalidated the reference keeps the stale list (numPrunedEdges == 0
+    // skips the swap, compute_csg.cpp:160) and ends up with duplicate keys whose winner depends
+    // on hash order; here the evident intent: the surviving list is empty.  DESIGN.md "deviations".
+    const unsigned int newE = kept + created;
+    int *newKeys = nullptr;
+    float4 *newInfo = nullptr;
+    if (newE) {
+        CU(cudaMalloc((void **)&newKeys, (size_t)newE * sizeof(int)));
+        CU(cudaMalloc((void **)&newInfo, (size_t)newE * sizeof(float4)));
+        CU(cudaMemsetAsync(ctx->d_csgCounts.p + 4, 0, 2 * sizeof(unsigned int), st));
+        StageTimer t(ctx, LVN_STAGE_CSG, 1);
+        launch_csg_emit(d, cd, ctx->d_ops.p, numOps, fe.d_field, ctx->d_touched.p, fe.d_keys, fe.d_info, fe.numEdges,
+                        (int)kept, newKeys, newInfo, ctx->d_csgCounts.p + 4, st);
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    collect_stage_times(ctx);
+    if (fe.d_keys) cudaFree(fe.d_keys);
+    if (fe.d_info) cudaFree(fe.d_info);
+    fe.d_keys = newKeys;
+    fe.d_info = newInfo;
+    fe.numEdges = (int)newE;
+    if (newE) LV(build_cuckoo(ctx, (const unsigned int *)fe.d_keys, newE, &fe.d_table, &fe.prime, fe.params, &fe.cuckooRetries));
+    return LVN_SUCCESS;
+}
+
+static bool aabb_overlaps(const lvn_aabb &a, const lvn_aabb &b)   // AABB::overlaps, aabb.h:24-33
+{
+    return !(a.max[0] < b.min[0] || a.max[1] < b.min[1] || a.max[2] < b.min[2] ||
+             a.min[0] > b.max[0] || a.min[1] > b.max[1] || a.min[2] > b.max[2]);
+}
+
+// LoadDensityField, compute_density_field.cpp:235-274.  Returns the cache entry, or nullptr in
+// *out when the chunk is a plain default field that never needs to persist.
+static int load_density_field(lvn_meshgen *ctx, const int32_t min[3], int size, bool forceEntry, FieldEntry **out)
+{
+    *out = nullptr;
+    const Key key = make_key(min, size);
+    auto it = ctx->fields.find(key);
+    const int startOp = it != ctx->fields.end() ? it->second.lastCSGOperation : 0;
+    lvn_aabb bb;
+    for (int k = 0; k < 3; k++) { bb.min[k] = min[k]; bb.max[k] = min[k] + size; }
+    std::vector<lvn_csg_operation_info> replay;
+    for (size_t i = (size_t)startOp; i < g.storedOps.size(); i++)
+        if (aabb_overlaps(bb, g.storedAABBs[i])) replay.push_back(g.storedOps[i]);
+    if (it == ctx->fields.end()) {
+        if (replay.empty() && !forceEntry) return LVN_SUCCESS;
+        FieldEntry fe;
+        const int rc = materialise_default_field(ctx, min, size, fe);
+        if (rc < 0) { fe.release(); return rc; }
+        it = ctx->fields.emplace(key, fe).first;
+    }
+    FieldEntry &fe = it->second;
+    fe.lastCSGOperation = (int)g.storedOps.size();
+    if (!replay.empty()) LV(apply_csg_to_field(ctx, replay.data(), (int)replay.size(), min, size, fe));
+    *out = &fe;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_apply_csg_operations(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
+                                                const int32_t clipmapNodeMin[3], int clipmapNodeSize)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!ctx || numOps < 0 || (numOps > 0 && !ops)) return LVN_ERR_INVALID_VALUE;
+    FieldEntry *fe = nullptr;
+    LV(load_density_field(ctx, clipmapNodeMin, clipmapNodeSize, true, &fe));
+    LV(apply_csg_to_field(ctx, ops, numOps, clipmapNodeMin, clipmapNodeSize, *fe));
+    fe->lastCSGOperation += numOps;   // compute_csg.cpp:237
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_apply_csg_operations_batch(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
+                                                      int nChunks, const int32_t *chunkMinSize)
+{
+    for (int i = 0; i < nChunks; i++)
+        LV(lvn_meshgen_apply_csg_operations(ctx, ops, numOps, &chunkMinSize[4 * i], chunkMinSize[4 * i + 3]));
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_free_chunk_octree(lvn_meshgen *ctx, const int32_t min[3], int size)
+{
+    if (!ctx) return LVN_ERR_INVALID_VALUE;
+    auto it = ctx->octrees.find(make_key(min, size));
+    if (it != ctx->octrees.end()) {
+        it->second.release();
+        ctx->octrees.erase(it);
+    }
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_is_chunk_empty(lvn_meshgen *ctx, const int32_t min[3], int size, int *isEmpty)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!ctx || !isEmpty) return LVN_ERR_INVALID_VALUE;
+    // Compute_ChunkIsEmpty (compute_density_field.cpp:278-299): cached field, else generate the
+    // default field and store it -- stored CSG operations are NOT replayed on this path
+    auto it = ctx->fields.find(make_key(min, size));
+    if (it == ctx->fields.end()) {
+        FieldEntry fe;
+        const int rc = materialise_default_field(ctx, min, size, fe);
+        if (rc < 0) { fe.release(); return rc; }
+        it = ctx->fields.emplace(make_key(min, size), fe).first;
+    }
+    *isEmpty = it->second.numEdges == 0;
+    return LVN_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// generateChunkMesh (compute_octree.cpp:351-375) with LoadOctree's cache (:154-181)
+// ---------------------------------------------------------------------------
+extern "C" int lvn_meshgen_generate_chunk_mesh(lvn_meshgen *ctx, const int32_t min[3], int clipmapNodeSize,
+                                               lvn_mesh_vertex *vertices, int vertexCapacity, int *numVertices,
+                                               lvn_mesh_triangle *triangles, int triangleCapacity, int *numTriangles,
+                                               lvn_seam_node_info *seamNodes, int seamCapacity, int *numSeamNodes)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!ctx || !numVertices || !numTriangles || !numSeamNodes) return LVN_ERR_INVALID_VALUE;
+    *numVertices = *numTriangles = *numSeamNodes = 0;
+    cudaStream_t st = ctx->stream;
+    const Key key = make_key(min, clipmapNodeSize);
+    auto oit = ctx->octrees.find(key);
+    if (oit == ctx->octrees.end()) {
+        FieldEntry *fe = nullptr;
+        LV(load_density_field(ctx, min, clipmapNodeSize, false, &fe));
+        int32_t ms[4] = {min[0], min[1], min[2], clipmapNodeSize};
+        BatchOpts opts;
+        LV(run_batch(ctx, 1, ms, opts));
+        const ChunkHdr h = ctx->h_hdrs.p[0];
+        if (h.E == 0) return LVN_SUCCESS;   // "no point in trying to construct the octree"
+        OctreeEntry oe;
+        oe.numNodes = h.N; oe.numQuads = h.Q; oe.numSeams = h.S;
+        if (h.N) {
+            CU(cudaMalloc((void **)&oe.d_v, (size_t)h.N * sizeof(lvn_mesh_vertex)));
+            CU(cudaMemcpyAsync(oe.d_v, ctx->d_vertices.p + h.nodeBase, (size_t)h.N * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToDevice, st));
+        }
+        if (h.Q) {
+            CU(cudaMalloc((void **)&oe.d_t, (size_t)h.Q * 6 * sizeof(int)));
+            CU(cudaMemcpyAsync(oe.d_t, ctx->d_tris.p + (size_t)h.quadBase * 6, (size_t)h.Q * 6 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        }
+        if (h.S) {
+            CU(cudaMalloc((void **)&oe.d_s, (size_t)h.S * sizeof(lvn_seam_node_info)));
+            CU(cudaMemcpyAsync(oe.d_s, ctx->d_seams.p + h.seamBase, (size_t)h.S * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToDevice, st));
+        }
+        oit = ctx->octrees.emplace(key, oe).first;
+    }
+    const OctreeEntry &oe = oit->second;
+    // no quads -> the mesh buffer stays empty (compute_octree.cpp:227-232); seams are still gathered
+    const int nV = oe.numQuads > 0 ? oe.numNodes : 0, nT = 2 * oe.numQuads, nS = oe.numSeams;
+    *numVertices = nV; *numTriangles = nT; *numSeamNodes = nS;
+    if (nV > vertexCapacity || nT > triangleCapacity || nS > seamCapacity) return LVN_ERR_CAPACITY;
+    if ((nV && !vertices) || (nT && !triangles) || (nS && !seamNodes)) return LVN_ERR_INVALID_VALUE;
+    if (nV) CU(cudaMemcpyAsync(vertices, oe.d_v, (size_t)nV * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToHost, st));
+    if (nT) CU(cudaMemcpyAsync(triangles, oe.d_t, (size_t)nT * sizeof(lvn_mesh_triangle), cudaMemcpyDeviceToHost, st));
+    if (nS) CU(cudaMemcpyAsync(seamNodes, oe.d_s, (size_t)nS * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return LVN_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// per-stage dump
+// ---------------------------------------------------------------------------
+extern "C" int lvn_meshgen_debug_dump_chunk(lvn_meshgen *ctx, const int32_t min[3], int size, lvn_stage_dump *dump)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!ctx || !dump) return LVN_ERR_INVALID_VALUE;
+    const Dims &d = ctx->dims;
+    const size_t F3 = (size_t)d.F * d.F * d.F;
+    cudaStream_t st = ctx->stream;
+    FieldEntry *fe = nullptr;
+    LV(load_density_field(ctx, min, size, false, &fe));
+    int32_t ms[4] = {min[0], min[1], min[2], size};
+    BatchOpts opts;
+    opts.debug = true;
+    LV(run_batch(ctx, 1, ms, opts));
+    const ChunkHdr h = ctx->h_hdrs.p[0];
+    dump->numEdges = h.E; dump->numNodes = h.N; dump->numTriangles = 2 * h.Q; dump->numSeamNodes = h.S;
+    if (h.E > dump->edgeCapacity || h.N > dump->nodeCapacity) return LVN_ERR_CAPACITY;
+    if (dump->materials) {
+        if (fe) {
+            CU(cudaMemcpyAsync(dump->materials, fe->d_field, F3, cudaMemcpyDeviceToHost, st));
+        } else if (g.densityKind != 0) {
+            CU(cudaMemcpyAsync(dump->materials, ctx->d_tmpFields.p, F3, cudaMemcpyDeviceToHost, st));
+        } else {
+            LV(ctx->d_tmpFields.reserve(F3));
+            LV(ctx->d_fieldPtrs.reserve(1));
+            CU(cudaMemcpyAsync(ctx->d_fieldPtrs.p, &ctx->d_tmpFields.p, sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
+            launch_field_from_heights(d, ctx->d_descs.p, 1, ctx->d_heights.p, g.defaultMaterial, ctx->d_fieldPtrs.p, st);
+            CU(cudaMemcpyAsync(dump->materials, ctx->d_tmpFields.p, F3, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (h.E) {
+        const int *keys = fe ? fe->d_keys : ctx->d_edgeKeys.p + h.edgeBase;
+        const float4 *info = fe ? fe->d_info : ctx->d_edgeInfo.p + h.edgeBase;
+        if (dump->edgeKeys) CU(cudaMemcpyAsync(dump->edgeKeys, keys, (size_t)h.E * 4, cudaMemcpyDeviceToHost, st));
+        if (dump->edgeInfo) CU(cudaMemcpyAsync(dump->edgeInfo, info, (size_t)h.E * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (h.N) {
+        const size_t b = (size_t)h.nodeBase, N = (size_t)h.N;
+        if (dump->nodeCodes) CU(cudaMemcpyAsync(dump->nodeCodes, ctx->d_dbgCodes.p + b, N * 4, cudaMemcpyDeviceToHost, st));
+        if (dump->nodeEdgeMasks) CU(cudaMemcpyAsync(dump->nodeEdgeMasks, ctx->d_dbgMasks.p + b, N * 4, cudaMemcpyDeviceToHost, st));
+        if (dump->nodeMaterials) CU(cudaMemcpyAsync(dump->nodeMaterials, ctx->d_dbgMats.p + b, N * 4, cudaMemcpyDeviceToHost, st));
+        if (dump->nodeQEFs) CU(cudaMemcpyAsync(dump->nodeQEFs, ctx->d_dbgQefs.p + b * 16, N * 64, cudaMemcpyDeviceToHost, st));
+        if (dump->nodePositions) CU(cudaMemcpyAsync(dump->nodePositions, ctx->d_dbgPos.p + b, N * 16, cudaMemcpyDeviceToHost, st));
+        if (dump->nodeNormals) CU(cudaMemcpyAsync(dump->nodeNormals, ctx->d_dbgNrm.p + b, N * 16, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return LVN_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// utilities (a9, a15)
+// ---------------------------------------------------------------------------
+extern "C" int lvn_find_next_prime(int n) { return host_find_next_prime(n); }
+
+extern "C" int lvn_exclusive_scan(const int32_t *data, int32_t *scan, int count)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (count < 0 || (count > 0 && (!data || !scan))) return LVN_ERR_INVALID_VALUE;
+    if (count == 0) return 0;
+    DevBuf<int> d_in, d_out, d_sums, d_total;
+    int total = 0, rc = LVN_SUCCESS;
+    auto body = [&]() -> int {
+        LV(d_in.reserve(count)); LV(d_out.reserve(count));
+        LV(d_sums.reserve(scan_block_sums_needed(count))); LV(d_total.reserve(1));
+        CU(cudaMemcpy(d_in.p, data, (size_t)count * 4, cudaMemcpyHostToDevice));
+        launch_exclusive_scan(d_in.p, d_out.p, count, d_sums.p, d_total.p, 0);
+        CU(cudaMemcpy(scan, d_out.p, (size_t)count * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&total, d_total.p, 4, cudaMemcpyDeviceToHost));
+        return LVN_SUCCESS;
+    };
+    rc = body();
+    d_in.release(); d_out.release(); d_sums.release(); d_total.release();
+    return rc < 0 ? rc : total;
+}
+
+extern "C" int lvn_compact_index_array(const int32_t *values, const int32_t *valid, int count, int32_t *out)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (count < 0 || (count > 0 && (!values || !valid || !out))) return LVN_ERR_INVALID_VALUE;
+    if (count == 0) return 0;
+    DevBuf<int> d_val, d_valid, d_scan, d_out, d_sums, d_total;
+    int total = 0, rc = LVN_SUCCESS;
+    auto body = [&]() -> int {
+        LV(d_val.reserve(count)); LV(d_valid.reserve(count)); LV(d_scan.reserve(count)); LV(d_out.reserve(count));
+        LV(d_sums.reserve(scan_block_sums_needed(count))); LV(d_total.reserve(1));
+        CU(cudaMemcpy(d_val.p, values, (size_t)count * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_valid.p, valid, (size_t)count * 4, cudaMemcpyHostToDevice));
+        launch_exclusive_scan(d_valid.p, d_scan.p, count, d_sums.p, d_total.p, 0);
+        launch_compact(d_val.p, d_valid.p, d_scan.p, count, d_out.p, 0);
+        CU(cudaMemcpy(&total, d_total.p, 4, cudaMemcpyDeviceToHost));
+        if (total > 0) CU(cudaMemcpy(out, d_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
+        return LVN_SUCCESS;
+    };
+    rc = body();
+    d_val.release(); d_valid.release(); d_scan.release(); d_out.release(); d_sums.release(); d_total.release();
+    return rc < 0 ? rc : total;
+}
+
+extern "C" int lvn_remove_duplicates(const int32_t *values, int count, int32_t *out)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (count < 0 || (count > 0 && (!values || !out))) return LVN_ERR_INVALID_VALUE;
+    if (count == 0) return 0;
+    for (int i = 0; i < count; i++) if (values[i] == -1) return LVN_ERR_INVALID_VALUE;   // -1 marks an empty slot
+    const unsigned int tableSize = (unsigned int)host_find_next_prime(count * 2);   // compute.cpp:462
+    DevBuf<int> d_val, d_out;
+    DevBuf<unsigned int> d_table, d_count;
+    unsigned int unique = 0;
+    int rc = LVN_SUCCESS;
+    auto body = [&]() -> int {
+        LV(d_val.reserve(count)); LV(d_out.reserve(count)); LV(d_table.reserve(tableSize)); LV(d_count.reserve(1));
+        CU(cudaMemcpy(d_val.p, values, (size_t)count * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemset(d_table.p, 0xff, (size_t)tableSize * 4));
+        CU(cudaMemset(d_count.p, 0, 4));
+        launch_dedupe(d_val.p, count, d_table.p, tableSize, d_out.p, d_count.p, 0);
+        CU(cudaMemcpy(&unique, d_count.p, 4, cudaMemcpyDeviceToHost));
+        if (unique) CU(cudaMemcpy(out, d_out.p, (size_t)unique * 4, cudaMemcpyDeviceToHost));
+        return LVN_SUCCESS;
+    };
+    rc = body();
+    d_val.release(); d_out.release(); d_table.release(); d_count.release();
+    return rc < 0 ? rc : (int)unique;
+}
+
+struct lvn_cuckoo {
+    unsigned long long *d_table = nullptr;
+    unsigned int prime = 0;
+    unsigned int params[8] = {0};
+    unsigned int tableSize = 0;
+    int retries = 0;
+    int insertedKeys = 0;
+};
+
+extern "C" lvn_cuckoo *lvn_cuckoo_create(unsigned int tableSize)
+{
+    if (!g.initialised) return nullptr;
+    lvn_cuckoo *t = new lvn_cuckoo;
+    t->tableSize = tableSize;
+    t->prime = (unsigned int)host_find_next_prime((int)std::max(2048u, tableSize * 2u));
+    if (cudaMalloc((void **)&t->d_table, (size_t)t->prime * 8) != cudaSuccess) { delete t; return nullptr; }
+    launch_fill_u64(t->d_table, t->prime, ~0ull, 0);
+    draw_cuckoo_params(t->params);
+    return t;
+}
+
+extern "C" int lvn_cuckoo_insert_keys(lvn_cuckoo *t, const uint32_t *keys, unsigned int count)
+{
+    if (!t || (count && !keys)) return LVN_ERR_INVALID_VALUE;
+    if (!count) return LVN_SUCCESS;
+    DevBuf<unsigned int> d_keys, d_failed;
+    int rc = LVN_CL_ERROR;
+    auto body = [&]() -> int {
+        LV(d_keys.reserve(count)); LV(d_failed.reserve(1));
+        CU(cudaMemcpy(d_keys.p, keys, (size_t)count * 4, cudaMemcpyHostToDevice));
+        for (int attempt = 0; attempt < 64; attempt++) {
+            if (attempt) {   // rehash with fresh parameters, compute_cuckoo.cpp:93-109
+                draw_cuckoo_params(t->params);
+                launch_fill_u64(t->d_table, t->prime, ~0ull, 0);
+                t->retries++;
+            }
+            CU(cudaMemset(d_failed.p, 0, 4));
+            launch_cuckoo_insert(d_keys.p, count, t->d_table, t->prime, t->params, d_failed.p, 0);
+            unsigned int failed = 0;
+            CU(cudaMemcpy(&failed, d_failed.p, 4, cudaMemcpyDeviceToHost));
+            if (!failed) { t->insertedKeys += (int)count; return LVN_SUCCESS; }
+        }
+        return LVN_CL_ERROR;
+    };
+    rc = body();
+    d_keys.release(); d_failed.release();
+    return rc;
+}
+
+extern "C" int lvn_cuckoo_find(const lvn_cuckoo *t, const uint32_t *keys, unsigned int count, uint32_t *values)
+{
+    if (!t || (count && (!keys || !values))) return LVN_ERR_INVALID_VALUE;
+    if (!count) return LVN_SUCCESS;
+    DevBuf<unsigned int> d_keys, d_vals;
+    auto body = [&]() -> int {
+        LV(d_keys.reserve(count)); LV(d_vals.reserve(count));
+        CU(cudaMemcpy(d_keys.p, keys, (size_t)count * 4, cudaMemcpyHostToDevice));
+        launch_cuckoo_find(d_keys.p, count, t->d_table, t->prime, t->params, d_vals.p, 0);
+        CU(cudaMemcpy(values, d_vals.p, (size_t)count * 4, cudaMemcpyDeviceToHost));
+        return LVN_SUCCESS;
+    };
+    const int rc = body();
+    d_keys.release(); d_vals.release();
+    return rc;
+}
+
+extern "C" int lvn_cuckoo_prime(const lvn_cuckoo *t) { return t ? (int)t->prime : 0; }
+extern "C" int lvn_cuckoo_retries(const lvn_cuckoo *t) { return t ? t->retries : 0; }
+extern "C" void lvn_cuckoo_destroy(lvn_cuckoo *t)
+{
+    if (!t) return;
+    if (t->d_table) cudaFree(t->d_table);
+    delete t;
+}

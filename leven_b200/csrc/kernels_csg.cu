@@ -1,0 +1,196 @@
+// CSG brush edits on a cached density field (a16).
+//
+// Reference functions restated (paths relative to the reference tree):
+//   BrushDensity / Density_Cuboid / Density_Sphere   leven/cl/apply_csg_operation.cl:42-82
+//   pR, fBox, vmax3                                  leven/cl/hg_sdf.glsl:164-166,218-221,460-463
+//   BrushMaterial / CSG_HermiteIndices / UpdateFieldMaterials   apply_csg_operation.cl:114-241
+//   FindUpdatedEdges ... PruneFieldEdges / CompactFieldEdges    apply_csg_operation.cl:253-437
+//   BrushZeroCrossing / BrushNormal / FindEdgeIntersectionInfo  apply_csg_operation.cl:86-175,443-477
+//   host sequence ApplyCSGOperations                 leven/src/compute_csg.cpp:11-220
+//
+// B200 shape of the same result: the reference builds the set of edges touching a changed
+// sample with 6-way expansion, compaction and a multi-round hash dedupe, then tests every old
+// edge against that list linearly (O(E*K)).  Here the set is a bitmap over the 3*H^3 Hermite
+// edges, so "dedupe" is an atomicOr and "prune" is one bit test per old edge.
+#include <float.h>
+
+#include "density.cuh"
+
+namespace lvn {
+
+__device__ __forceinline__ float length3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
+
+__device__ __forceinline__ float brush_density(float x, float y, float z, const CsgOpDev &op)
+{
+    const float lx = x - op.ox, ly = y - op.oy, lz = z - op.oz;
+    if (op.shape == 0) {
+        const float rx = op.c * lx + op.s * lz;      // pR on (x, z); cos/sin computed on the host
+        const float rz = op.c * lz + op.s * (-lx);
+        const float dx = fabsf(rx) - op.dx, dy = fabsf(ly) - op.dy, dz = fabsf(rz) - op.dz;
+        const float outside = length3(fmaxf(dx, 0.f), fmaxf(dy, 0.f), fmaxf(dz, 0.f));
+        const float inside = fmaxf(fmaxf(fminf(dx, 0.f), fminf(dy, 0.f)), fminf(dz, 0.f));
+        return outside + inside;
+    }
+    return length3(lx, ly, lz) - op.dx;
+}
+
+__device__ __forceinline__ int edge_bit_index(int x, int y, int z, int axis, int H)
+{
+    return (x + H * (y + H * z)) * 3 + axis;
+}
+
+// CSG_HermiteIndices + UpdateFieldMaterials + FindUpdatedEdges in one pass over the field
+__global__ void k_csg_materials(Dims d, ChunkDesc cd, const CsgOpDev *__restrict__ ops, int numOps,
+                                uint8_t *field, unsigned int *touched, unsigned int *numChanged)
+{
+    const int F = d.F, H = d.H, F3 = F * F * F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F3; i += gridDim.x * blockDim.x) {
+        const int x = i % F, y = (i / F) % F, z = i / (F * F);
+        const int oldMaterial = field[i];
+        const float wx = (float)(cd.ox + cd.scale * x), wy = (float)(cd.oy + cd.scale * y), wz = (float)(cd.oz + cd.scale * z);
+        int m = oldMaterial;
+        for (int k = 0; k < numOps; k++) {   // BrushMaterial: the last op with d <= 0 wins
+            const CsgOpDev op = ops[k];
+            if (brush_density(wx, wy, wz, op) <= 0.f) m = op.type == 0 ? op.material : LVN_MATERIAL_AIR;
+        }
+        if (m == oldMaterial) continue;
+        field[i] = (uint8_t)m;
+        atomicAdd(numChanged, 1u);
+        const int p[3] = {x, y, z};
+        if (x < H && y < H && z < H)
+            for (int k = 0; k < 3; k++) {
+                const int e = edge_bit_index(x, y, z, k, H);
+                atomicOr(&touched[e >> 5], 1u << (e & 31));
+            }
+        for (int k = 0; k < 3; k++) {
+            if (p[k] <= 0) continue;
+            const int qx = x - (k == 0), qy = y - (k == 1), qz = z - (k == 2);
+            if (qx < H && qy < H && qz < H) {
+                const int e = edge_bit_index(qx, qy, qz, k, H);
+                atomicOr(&touched[e >> 5], 1u << (e & 31));
+            }
+        }
+    }
+}
+
+void launch_csg_materials(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
+                          uint8_t *field, unsigned int *touchedBits, unsigned int *numChanged, cudaStream_t s)
+{
+    k_csg_materials<<<296, 256, 0, s>>>(d, desc, ops, numOps, field, touchedBits, numChanged);
+}
+
+__device__ __forceinline__ bool edge_sign_change(const uint8_t *__restrict__ field, int F, int x, int y, int z, int axis)
+{
+    const int m0 = field[x + F * (y + F * z)];
+    const int m1 = field[(x + (axis == 0)) + F * ((y + (axis == 1)) + F * (z + (axis == 2)))];
+    return (m0 == LVN_MATERIAL_AIR) != (m1 == LVN_MATERIAL_AIR);
+}
+
+__device__ __forceinline__ int key_to_bit(int key, const Dims &d)
+{
+    const int axis = key & 3, idx = key >> 2;
+    return edge_bit_index(idx & d.mask, (idx >> d.shift) & d.mask, (idx >> (d.shift * 2)) & d.mask, axis, d.H);
+}
+
+// counts[0] = old edges that survive the prune; counts[1] = touched edges that now change sign
+__global__ void k_csg_count(Dims d, const uint8_t *__restrict__ field, const unsigned int *__restrict__ touched,
+                            const int *__restrict__ oldKeys, int numOld, unsigned int *counts)
+{
+    const int H = d.H, numBits = 3 * H * H * H, numWords = (numBits + 31) / 32;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    unsigned int kept = 0, created = 0;
+    for (int i = gid; i < numOld; i += stride) {
+        const int e = key_to_bit(oldKeys[i], d);
+        if (!((touched[e >> 5] >> (e & 31)) & 1u)) kept++;
+    }
+    for (int w = gid; w < numWords; w += stride) {
+        unsigned int bits = touched[w];
+        while (bits) {
+            const int b = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int e = w * 32 + b, axis = e % 3, cell = e / 3;
+            const int x = cell % H, y = (cell / H) % H, z = cell / (H * H);
+            if (edge_sign_change(field, d.F, x, y, z, axis)) created++;
+        }
+    }
+    if (kept) atomicAdd(&counts[0], kept);
+    if (created) atomicAdd(&counts[1], created);
+}
+
+void launch_csg_count(const Dims &d, const uint8_t *field, const unsigned int *touchedBits,
+                      const int *oldKeys, int numOld, unsigned int *counts, cudaStream_t s)
+{
+    k_csg_count<<<148, 256, 0, s>>>(d, field, touchedBits, oldKeys, numOld, counts);
+}
+
+// PruneFieldEdges + CompactFieldEdges, then the CSG FindEdgeIntersectionInfo for created edges.
+// cursor[0] counts kept edges, cursor[1] created edges (appended after the kept ones: the
+// caller passes newKeys/newInfo and the final kept count is known from k_csg_count).
+__global__ void k_csg_emit(Dims d, ChunkDesc cd, const CsgOpDev *__restrict__ ops, int numOps,
+                           const uint8_t *__restrict__ field, const unsigned int *__restrict__ touched,
+                           const int *__restrict__ oldKeys, const float4 *__restrict__ oldInfo, int numOld,
+                           int numKept, int *__restrict__ newKeys, float4 *__restrict__ newInfo, unsigned int *cursor)
+{
+    const int H = d.H, numBits = 3 * H * H * H, numWords = (numBits + 31) / 32;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = gid; i < numOld; i += stride) {
+        const int key = oldKeys[i];
+        const int e = key_to_bit(key, d);
+        if ((touched[e >> 5] >> (e & 31)) & 1u) continue;
+        const unsigned int o = atomicAdd(&cursor[0], 1u);
+        newKeys[o] = key;
+        newInfo[o] = oldInfo[i];
+    }
+    for (int w = gid; w < numWords; w += stride) {
+        unsigned int bits = touched[w];
+        while (bits) {
+            const int b = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int e = w * 32 + b, axis = e % 3, cell = e / 3;
+            const int x = cell % H, y = (cell / H) % H, z = cell / (H * H);
+            if (!edge_sign_change(field, d.F, x, y, z, axis)) continue;
+            // FindEdgeIntersectionInfo, apply_csg_operation.cl:443-477
+            const int wx = (cd.scale * x) + cd.ox, wy = (cd.scale * y) + cd.oy, wz = (cd.scale * z) + cd.oz;
+            const float p0x = (float)wx, p0y = (float)wy, p0z = (float)wz;
+            const float p1x = (float)(wx + (axis == 0 ? cd.scale : 0)), p1y = (float)(wy + (axis == 1 ? cd.scale : 0)),
+                        p1z = (float)(wz + (axis == 2 ? cd.scale : 0));
+            // BrushZeroCrossing: first minimum of |density| over 17 steps x ops
+            float minDensity = FLT_MAX, crossing = 0.f;
+            for (float t = 0.f; t <= 1.f; t += (1.f / 16.f)) {
+                const float px = mixf(p0x, p1x, t), py = mixf(p0y, p1y, t), pz = mixf(p0z, p1z, t);
+                for (int k = 0; k < numOps; k++) {
+                    const float dd = fabsf(brush_density(px, py, pz, ops[k]));
+                    if (dd < minDensity) { crossing = t; minDensity = dd; }
+                }
+            }
+            const float px = mixf(p0x, p1x, crossing), py = mixf(p0y, p1y, crossing), pz = mixf(p0z, p1z, crossing);
+            // BrushNormal: the last op whose density at p is <= 0, flipped for subtract
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            const float h = 0.001f;
+            for (int k = 0; k < numOps; k++) {
+                const CsgOpDev op = ops[k];
+                if (brush_density(px, py, pz, op) > 0.f) continue;
+                float gx = brush_density(px + h, py, pz, op) - brush_density(px - h, py, pz, op);
+                float gy = brush_density(px, py + h, pz, op) - brush_density(px, py - h, pz, op);
+                float gz = brush_density(px, py, pz + h, op) - brush_density(px, py, pz - h, op);
+                const float flip = op.type == 0 ? 1.f : -1.f;
+                normalize3(gx, gy, gz);
+                nx = flip * gx; ny = flip * gy; nz = flip * gz;
+            }
+            const unsigned int o = (unsigned int)numKept + atomicAdd(&cursor[1], 1u);
+            newKeys[o] = ((x | (y << d.shift) | (z << (d.shift * 2))) << 2) | axis;
+            newInfo[o] = make_float4(nx, ny, nz, crossing);
+        }
+    }
+}
+
+void launch_csg_emit(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
+                          const uint8_t *field, const unsigned int *touchedBits,
+                          const int *oldKeys, const float4 *oldInfo, int numOld, int numKept,
+                          int *newKeys, float4 *newInfo, unsigned int *cursor, cudaStream_t s)
+{
+    k_csg_emit<<<148, 256, 0, s>>>(d, desc, ops, numOps, field, touchedBits, oldKeys, oldInfo, numOld,
+                                   numKept, newKeys, newInfo, cursor);
+}
+
+}  // namespace lvn

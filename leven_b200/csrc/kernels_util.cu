@@ -1,0 +1,286 @@
+// Utilities of the path: cuckoo hash (a9), scan / compact / dedupe / fill (a15).
+//
+// Reference functions restated (paths relative to the reference tree):
+//   Cuckoo_Hash / Cuckoo_InsertKeys / Cuckoo_Find   leven/cl/cuckoo.cl:18-104
+//   FindNextPrime                                   leven/src/primes.cpp:32-59
+//   ExclusiveLocalScan / WriteScannedOutput         leven/cl/scan.cl:2-121
+//   CompactIndexArray                               leven/cl/compact.cl:4-16
+//   RemoveDuplicates (+ duplicate.cl)               leven/src/compute.cpp:446-543
+//   FillBufferLong                                  leven/cl/fill_buffer.cl:17-27
+#include "lvn_internal.h"
+
+namespace lvn {
+
+// ---------------------------------------------------------------------------
+int host_find_next_prime(int n)
+{
+    auto isPrime = [](int x) {
+        int o = 4, i = 5;
+        for (;;) {
+            const int q = x / i;
+            if (q < i) return true;
+            if (x == q * i) return false;
+            o ^= 6;
+            i += o;
+        }
+    };
+    if (n <= 2) return 2;
+    if (n == 3) return 3;
+    if (n <= 5) return 5;
+    const int k = n / 6;
+    int i = n - 6 * k;
+    const int o = i < 2 ? 1 : 5;
+    int x = 6 * k + o;
+    for (i = (3 + o) / 2; !isPrime(x); x += i) i ^= 6;
+    return x;
+}
+
+// ---------------------------------------------------------------------------
+__global__ void k_fill_u64(unsigned long long *p, size_t n, unsigned long long v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t s)
+{
+    if (!n) return;
+    const int block = 256;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    k_fill_u64<<<grid > 1184 ? 1184 : grid, block, 0, s>>>(p, n, v);
+}
+
+// ---------------------------------------------------------------------------
+// cuckoo
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int cuckoo_hash(unsigned int key, unsigned int a, unsigned int b, unsigned int prime)
+{
+    const unsigned long long h = (unsigned long long)(unsigned int)(a * key);   // 32-bit wrap, cuckoo.cl:21
+    return (unsigned int)(((h + b) % 4294967291ull) % prime);
+}
+
+// One thread per key; the eviction chain is 32 atomic exchanges long (CUCKOO_MAX_ITERATIONS).
+// There is no stash: the reference's stash insert is out of bounds (cuckoo.cl:67-69), so a
+// chain that does not terminate is reported in *failed and the host rehashes the table, as the
+// reference host loop does for any key that was not inserted (compute_cuckoo.cpp:89-132).
+__global__ void k_cuckoo_insert(const unsigned int *__restrict__ keys, unsigned int count,
+                                unsigned long long *table, unsigned int prime,
+                                unsigned int a0, unsigned int b0, unsigned int a1, unsigned int b1,
+                                unsigned int a2, unsigned int b2, unsigned int a3, unsigned int b3,
+                                unsigned int *failed)
+{
+    const unsigned int index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index >= count) return;
+    unsigned int key = keys[index];
+    unsigned long long entry = ((unsigned long long)index << 32) | key;
+    unsigned int h = cuckoo_hash(key, a0, b0, prime);
+    for (int i = 0; i < 32; i++) {
+        entry = atomicExch(&table[h], entry);
+        if (entry == ~0ull) return;
+        key = (unsigned int)(entry & 0xffffffffull);
+        const unsigned int h0 = cuckoo_hash(key, a0, b0, prime), h1 = cuckoo_hash(key, a1, b1, prime),
+                           h2 = cuckoo_hash(key, a2, b2, prime), h3 = cuckoo_hash(key, a3, b3, prime);
+        if (h == h0) h = h1;
+        else if (h == h1) h = h2;
+        else if (h == h2) h = h3;
+        else if (h == h3) h = h0;
+    }
+    atomicAdd(failed, 1u);
+}
+
+void launch_cuckoo_insert(const unsigned int *keys, unsigned int count, unsigned long long *table,
+                          unsigned int prime, const unsigned int *p, unsigned int *failed, cudaStream_t s)
+{
+    if (!count) return;
+    k_cuckoo_insert<<<(count + 255) / 256, 256, 0, s>>>(keys, count, table, prime,
+                                                       p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], failed);
+}
+
+__global__ void k_cuckoo_find(const unsigned int *__restrict__ keys, unsigned int count,
+                              const unsigned long long *__restrict__ table, unsigned int prime,
+                              unsigned int a0, unsigned int b0, unsigned int a1, unsigned int b1,
+                              unsigned int a2, unsigned int b2, unsigned int a3, unsigned int b3,
+                              unsigned int *__restrict__ values)
+{
+    const unsigned int index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index >= count) return;
+    const unsigned int key = keys[index];
+    const unsigned int a[4] = {a0, a1, a2, a3}, b[4] = {b0, b1, b2, b3};
+    unsigned int value = ~0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const unsigned long long entry = table[cuckoo_hash(key, a[i], b[i], prime)];
+        if ((unsigned int)(entry & 0xffffffffull) == key) { value = (unsigned int)(entry >> 32); break; }
+    }
+    values[index] = value;
+}
+
+void launch_cuckoo_find(const unsigned int *keys, unsigned int count, const unsigned long long *table,
+                        unsigned int prime, const unsigned int *p, unsigned int *values, cudaStream_t s)
+{
+    if (!count) return;
+    k_cuckoo_find<<<(count + 255) / 256, 256, 0, s>>>(keys, count, table, prime,
+                                                     p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], values);
+}
+
+// ---------------------------------------------------------------------------
+// exclusive scan: 1024 threads x 4 items per block, block sums scanned by one block, then added
+// ---------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warpSums, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warpSums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warpSums[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warpSums[lane] = winc - w;
+        if (lane == 31) warpSums[32] = winc;
+    }
+    __syncthreads();
+    total = warpSums[32];
+    const int r = warpSums[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_tiles(const int *__restrict__ data, int *__restrict__ scan,
+                                                           int count, int *__restrict__ blockSums)
+{
+    __shared__ int warpSums[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < count) ? data[base + i] : 0; sum += v[i]; }
+    int total;
+    int run = block_exclusive_scan(sum, warpSums, total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < count) scan[base + i] = run; run += v[i]; }
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
+}
+
+// scans up to SCAN_TILE block sums in place (exclusive), writes the grand total
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_sums(int *blockSums, int numBlocks, int *total)
+{
+    __shared__ int warpSums[33];
+    int carry = 0;
+    for (int base = 0; base < numBlocks; base += SCAN_BLOCK) {
+        const int i = base + threadIdx.x;
+        const int v = i < numBlocks ? blockSums[i] : 0;
+        int t;
+        const int ex = block_exclusive_scan(v, warpSums, t);
+        if (i < numBlocks) blockSums[i] = carry + ex;
+        carry += t;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int *__restrict__ scan, int count, const int *__restrict__ blockSums)
+{
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int off = blockSums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < count) scan[base + i] += off;
+}
+
+int scan_block_sums_needed(int count) { return (count + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+void launch_exclusive_scan(const int *data, int *scan, int count, int *blockSums, int *total, cudaStream_t s)
+{
+    if (count <= 0) { cudaMemsetAsync(total, 0, sizeof(int), s); return; }
+    const int blocks = (count + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<blocks, SCAN_BLOCK, 0, s>>>(data, scan, count, blockSums);
+    k_scan_sums<<<1, SCAN_BLOCK, 0, s>>>(blockSums, blocks, total);
+    if (blocks > 1) k_scan_add<<<blocks, SCAN_BLOCK, 0, s>>>(scan, count, blockSums);
+}
+
+__global__ void k_compact(const int *__restrict__ values, const int *__restrict__ valid, const int *__restrict__ scan,
+                          int count, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && valid[i]) out[scan[i]] = values[i];
+}
+void launch_compact(const int *values, const int *valid, const int *scan, int count, int *out, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_compact<<<(count + 255) / 256, 256, 0, s>>>(values, valid, scan, count, out);
+}
+
+// ---------------------------------------------------------------------------
+// dedupe: one pass over an open-addressing hash set; the thread whose compare-and-swap claims
+// the slot is the "winner" (the reference runs winner/loser rounds over a last-writer-wins table)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int murmur_hash(unsigned int value)   // duplicate.cl:4-28
+{
+    unsigned int hash = value;
+    hash *= 0xcc9e2d51u;
+    hash = (hash << 15) | (hash >> 17);
+    hash *= 0x1b873593u;
+    hash ^= value;
+    hash = ((hash << 13) | (hash >> 19)) * 5u + 0xe6546b64u;
+    hash ^= (hash >> 16);
+    hash *= 0x85ebca6bu;
+    hash ^= (hash >> 13);
+    hash *= 0xc2b2ae35u;
+    hash ^= (hash >> 16);
+    return hash;
+}
+
+__global__ void k_dedupe(const int *__restrict__ values, int count, unsigned int *table, unsigned int tableSize,
+                         int *__restrict__ out, unsigned int *outCount)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned int value = (unsigned int)values[i];
+    unsigned int h = murmur_hash(value) % tableSize;
+    for (;;) {
+        const unsigned int old = atomicCAS(&table[h], 0xffffffffu, value);
+        if (old == 0xffffffffu) { out[atomicAdd(outCount, 1u)] = (int)value; return; }
+        if (old == value) return;
+        h = h + 1 == tableSize ? 0 : h + 1;
+    }
+}
+void launch_dedupe(const int *values, int count, unsigned int *table, unsigned int tableSize,
+                   int *out, unsigned int *outCount, cudaStream_t s)
+{
+    if (count <= 0) return;
+    k_dedupe<<<(count + 255) / 256, 256, 0, s>>>(values, count, table, tableSize, out, outCount);
+}
+
+// ---------------------------------------------------------------------------
+// FP32 roofline denominator: 8 independent FMA chains per thread
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fma_peak(float *sink, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.9999f, c = 1e-4f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+            a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+        }
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678f) sink[0] = r;   // never true; keeps the chains alive
+}
+void launch_fma_peak(float *sink, int iters, int blocks, cudaStream_t s)
+{
+    k_fma_peak<<<blocks, 256, 0, s>>>(sink, iters);
+}
+
+}  // namespace lvn

@@ -1,0 +1,135 @@
+// Internal types shared by the CUDA translation units of libleven_b200.so.
+// Nothing here crosses the C ABI (include/leven_compute.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/leven_compute.h"
+
+namespace lvn {
+
+// One requested chunk of a batch.  Filled on the host, read by every stage kernel.
+struct ChunkDesc {
+    int ox, oy, oz;        // field offset in voxel units = min / LEAF_SIZE_SCALE (compute.cpp:569-577)
+    int scale;             // sampleScale = size / (V * 4) (compute_density_field.cpp:149)
+    int minx, miny, minz;  // world-space chunk min (SolveQEFs' worldSpaceOffset, compute_octree.cpp:131)
+    int size;
+    int colSet;            // SRC_HEIGHTS: index of this chunk's column-height set
+    int source;            // SRC_*
+    int edgeMode;          // EDGES_*
+    int cachedNumEdges;    // EDGES_CACHED
+    const uint8_t *field;  // SRC_FIELD: u8 materials, F^3
+    const int *cachedKeys;           // EDGES_CACHED: the field's edge list (arbitrary order)
+    const float4 *cachedInfo;
+    const unsigned long long *cuckooTable;   // edge key -> slot in cachedKeys (a9)
+    unsigned int cuckooPrime;
+    unsigned int cuckooParams[8];
+    float colour[3];       // ColourForMinLeafSize(size / 256) (clipmap.cpp:329-352)
+    int pad;
+};
+
+enum { SRC_HEIGHTS = 0, SRC_FIELD = 1 };
+enum { EDGES_FRESH = 0, EDGES_CACHED = 1 };
+
+// Per-chunk counts and arena placement, written by the classify kernel.
+struct ChunkHdr {
+    int E, N, Q, S;                          // edges, nodes (= vertices), quads, seam nodes
+    int edgeBase, nodeBase, quadBase, seamBase;
+    int status;                              // 0, or LVN_ERR_CAPACITY when an arena overflowed
+    int Ey;                                  // y-axis edges among E (stage accounting)
+    int pad[2];
+};
+
+struct ArenaCounters {
+    unsigned int edges, nodes, quads, seams;
+    unsigned int overflow;
+    unsigned int nonEmpty;
+    unsigned int pad[2];
+};
+
+struct ArenaCaps { unsigned int edges, nodes, quads, seams; };
+
+// Geometry of a mesh-generation context (compute.cpp:245-252,271).
+struct Dims {
+    int V, H, F;        // voxels per chunk, Hermite grid (V+1), field samples (V+2)
+    int shift, mask;    // VOXEL_INDEX_SHIFT / MASK
+    int depth;          // MAX_OCTREE_DEPTH
+};
+
+// Per-chunk scratch that links the classify kernel to the leaf kernel.
+struct ChunkScratch {
+    unsigned long long *bitsLo;   // [n][F*F] solid bits x 0..63 of row (z*F + y)
+    unsigned int *bitsHi;         // [n][F*F] solid bits x 64..
+    unsigned int *rowE;           // [n][H*H] exclusive edge offsets per Hermite row (z*H + y)
+    unsigned int *rowN;           // [n][V*V] exclusive node offsets per voxel row (z*V + y)
+    unsigned int *rowQ;           // [n][V*V] quads
+    unsigned int *rowS;           // [n][V*V] seam nodes
+};
+
+struct DensityParams {
+    const float2 *grad2;      // [256*256] snoise2 gradients (texel.xy * 4 - 1)
+    const float4 *grad3;      // [256*256] snoise3 gradients xyz, w = bits of the perm column
+    int kind;                 // 0 terrain, 1 stress
+    float param;              // stress threshold
+    int defaultMaterial;
+};
+
+// Optional per-node stage outputs (parity dumps and the octree cache).
+struct NodeDebug {
+    unsigned int *codes;
+    int *edgeMasks;
+    int *matWords;
+    float *qefs;       // 16 floats per node
+    float4 *positions;
+    float4 *normals;
+};
+
+// ---- launchers (kernels_chunk.cu) ----------------------------------------
+void launch_columns(const DensityParams &dp, const Dims &d, const int4 *colSetOrigins, int numColSets,
+                    float *heights, cudaStream_t s);
+void launch_field_from_heights(const Dims &d, const ChunkDesc *descs, int n, const float *heights,
+                               int defaultMaterial, uint8_t *const *fields, cudaStream_t s);
+void launch_field_density(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, int n,
+                          uint8_t *const *fields, cudaStream_t s);
+void launch_classify(const Dims &d, const ChunkDesc *descs, int n, const float *heights,
+                     ChunkHdr *hdrs, ChunkScratch ws, ArenaCounters *counters, ArenaCaps caps,
+                     int *edgeKeys, cudaStream_t s);
+void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, int n,
+                    const ChunkHdr *hdrs, const float *heights, const int *edgeKeys, float4 *edgeInfo,
+                    cudaStream_t s);
+void launch_leaves(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, int n,
+                   const ChunkHdr *hdrs, ChunkScratch ws, const float4 *edgeInfo,
+                   lvn_mesh_vertex *vertices, int *triIndices, lvn_seam_node_info *seams,
+                   NodeDebug dbg, cudaStream_t s);
+
+// ---- launchers (kernels_csg.cu) -------------------------------------------
+struct CsgOpDev {          // CSGOperation + host-computed cos/sin of rotateY
+    int type, shape, material, pad;
+    float ox, oy, oz, dx, dy, dz, c, s;
+};
+void launch_csg_materials(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
+                          uint8_t *field, unsigned int *touchedBits, unsigned int *numChanged, cudaStream_t s);
+void launch_csg_count(const Dims &d, const uint8_t *field, const unsigned int *touchedBits,
+                      const int *oldKeys, int numOld, unsigned int *counts /* kept, created */, cudaStream_t s);
+void launch_csg_emit(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
+                     const uint8_t *field, const unsigned int *touchedBits,
+                     const int *oldKeys, const float4 *oldInfo, int numOld, int numKept,
+                     int *newKeys, float4 *newInfo, unsigned int *cursor, cudaStream_t s);
+
+// ---- launchers (kernels_util.cu) -------------------------------------------
+int  host_find_next_prime(int n);
+void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t s);
+void launch_cuckoo_insert(const unsigned int *keys, unsigned int count, unsigned long long *table,
+                          unsigned int prime, const unsigned int *params8, unsigned int *failed, cudaStream_t s);
+void launch_cuckoo_find(const unsigned int *keys, unsigned int count, const unsigned long long *table,
+                        unsigned int prime, const unsigned int *params8, unsigned int *values, cudaStream_t s);
+// device-wide exclusive scan of ints; total written to *total (device)
+void launch_exclusive_scan(const int *data, int *scan, int count, int *blockSums, int *total, cudaStream_t s);
+int  scan_block_sums_needed(int count);
+void launch_compact(const int *values, const int *valid, const int *scan, int count, int *out, cudaStream_t s);
+void launch_fma_peak(float *sink, int iters, int blocks, cudaStream_t s);
+void launch_dedupe(const int *values, int count, unsigned int *table, unsigned int tableSize,
+                   int *out, unsigned int *outCount, cudaStream_t s);
+
+}  // namespace lvn

@@ -1,0 +1,100 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/leven_compute.h declares, and the POD layouts are the reference's."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "leven_compute.h")
+
+
+def _declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lvn_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    import leven_b200.compute as lc
+    L = lc.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in leven_compute.h but not exported"
+    assert set(declared) == set(lc.ABI.keys())
+
+
+def test_no_torch_or_oracle_in_product():
+    """the product never routes through the oracle (or any CPU fallback)"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "leven_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+                assert "lvo_" not in src
+
+
+def test_pod_layouts(built):
+    """sizeof/offsetof from the C header via gcc == the reference PODs == the numpy dtypes"""
+    import leven_b200.compute as lc
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "leven_compute.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(lvn_csg_operation_info), sizeof(lvn_seam_node_info),
+         sizeof(lvn_mesh_vertex), sizeof(lvn_mesh_triangle), sizeof(lvn_aabb), sizeof(lvn_chunk_result));
+  printf("%zu %zu %zu\n", offsetof(lvn_csg_operation_info, origin), offsetof(lvn_csg_operation_info, dimensions),
+         offsetof(lvn_seam_node_info, position));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = subprocess.check_output([exe]).decode().split()
+    sizes = list(map(int, out))
+    # CSGOperationInfo 48 (compute.h:16-24), SeamNodeInfo 48 (compute.h:26-31), MeshVertex 48
+    # (render_types.h:24-39), MeshTriangle 12 (render_types.h:42-58), AABB 24 (aabb.h:95-96)
+    assert sizes[:6] == [48, 48, 48, 12, 24, 32]
+    assert sizes[6:] == [16, 32, 16]
+    assert C.sizeof(lc.CSGOperationInfo) == 48 and C.sizeof(lc.AABB) == 24
+    assert lc.MeshVertex.itemsize == 48 and lc.MeshTriangle.itemsize == 12 and lc.SeamNodeInfo.itemsize == 48
+    assert lc.ChunkResult.itemsize == 32
+
+
+def test_cpp_shim_compiles(built):
+    """the header-only C++ shim (compute.h's own class on top of the C ABI) compiles as C++11"""
+    prog = r'''
+#include "leven_compute.hpp"
+int main() {
+  static_assert(sizeof(CSGOperationInfo) == 48, "CSGOperationInfo");
+  static_assert(sizeof(SeamNodeInfo) == 48, "SeamNodeInfo");
+  static_assert(sizeof(MeshVertex) == 48, "MeshVertex");
+  static_assert(sizeof(MeshTriangle) == 12, "MeshTriangle");
+  Compute_MeshGenContext* (*create)(const int) = &Compute_MeshGenContext::create;
+  (void)create;
+  return GetCLErrorString(0) == nullptr;
+}'''
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.cpp")
+        open(src, "w").write(prog)
+        subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src])
+
+
+def test_no_device_fails_loudly(built):
+    """without a CUDA device the product reports LVN_ERR_NO_DEVICE; it never computes on the CPU"""
+    import leven_b200.compute as lc
+    import torch
+    if torch.cuda.is_available():
+        return
+    assert lc.Compute_Initialise(1, 0, 2) == lc.LVN_ERR_NO_DEVICE
+    assert lc.Compute_MeshGenContext.create(64).privateCtx_ is None
+    assert lc.GetCLErrorString(lc.LVN_ERR_NO_DEVICE) == "LVN_ERR_NO_DEVICE"
+    assert lc.FindNextPrime(2048) == 2053        # host-only helper works anywhere
