@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- 64^3 DC chunks/sec (density -> Hermite -> active voxels -> QEF -> mesh).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the whole hot path over one batch: BASELINE.json configs[1], the
+clipmap LOD0 ring of 8x8x8 = 512 chunks of 64^3 default noise terrain.  With N GPUs every rank
+meshes its own 512-chunk ring (rank r is shifted by 8r chunks in x), no data-path collective:
+weak scaling, value = N*512*K chunks / max-over-ranks device time.
+
+  value   : kernels + the per-batch count read-back, results left resident in HBM
+  e2e     : the same pass through the host-facing C ABI call (lvn_meshgen_generate_batch): chunk
+            list uploaded, every mesh / seam arena copied back into pinned host memory, all
+            inside the timed region
+  roofline: the dominant kernel (Hermite, FP32-bound), algorithmic flops of SURVEY.md 8(d)
+            over its CUDA-event time, against the FP32 peak measured in the same run
+  cpu_baseline / --impl reference: the oracle port of the reference pipeline on the host cores
+            (the reference itself is OpenCL and cannot run here: no ICD)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 93923590          # leven/default.cfg:8
+V = 64
+SIZE = 256               # LOD0 chunk: 64 voxels * LEAF_SIZE_SCALE
+CY0 = 9                  # floor(h(0,0) / 64): h(0,0) = 598.49 voxels for this seed (checked below)
+RING = 8                 # 8 x 8 x 8 chunks
+FLOP_PER_DENSITY = 1217
+METRIC = "64^3 DC chunks/sec (density->QEF->mesh)"
+
+
+def ring_chunks(rank):
+    h = RING // 2
+    return np.array([[(cx + RING * rank) * SIZE, (CY0 + dy) * SIZE, cz * SIZE, SIZE]
+                     for dy in range(-h, h) for cz in range(-h, h) for cx in range(-h, h)], np.int32)
+
+
+def workload_name():
+    return (f"configs[1]: clipmap LOD0 ring, {RING}x{RING}x{RING}={RING ** 3} chunks of 64^3 default noise terrain "
+            f"(seed {SEED}) per GPU, one batch per step")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_reference(args, rank):
+    """reference arm: the oracle port (oracle/) of the reference's CPU-side pipeline on all host
+    threads, same workload; rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    world = O.World(seed=SEED, default_material=0, voxels_per_chunk=V)
+    ms = ring_chunks(0)
+    threads = 1
+    for _ in range(args.warmup if args.warmup < 2 else 1):      # one warm pass is enough on the CPU
+        _, threads = world.batch_counts(ms[:64])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        counts, threads = world.batch_counts(ms)
+    dt = time.perf_counter() - t0
+    value = len(ms) * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name()},
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": int(threads), "kind": "port",
+                         "sample": f"all {len(ms)} chunks of the workload per step, OpenMP over chunks; "
+                                   f"{int((counts[:, 1] > 0).sum())} contain surface"},
+        "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import leven_b200.compute as lc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world_size == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world_size == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    assert lc.Compute_SetDevice(local_rank) == 0
+    rc = lc.Compute_Initialise(SEED, 0, 2)
+    assert rc == 0, f"Compute_Initialise: {lc.GetCLErrorString(rc)} {lc.last_cuda_error()}"
+    ctx = lc.Compute_MeshGenContext.create(V)
+    assert ctx.privateCtx_
+    stream = torch.cuda.current_stream()
+    ctx.setStream(stream.cuda_stream)        # so that torch.cuda.Event brackets the kernels
+    ms = ring_chunks(rank)
+    nchunks = len(ms)
+
+    # sizing pass (also validates CY0: the origin stack's surface chunk is non-empty)
+    rc, res, view = ctx.generateBatchDevice(ms)
+    assert rc == 0, f"generateBatchDevice: {lc.GetCLErrorString(rc)} {lc.last_cuda_error()}"
+    if rank == 0:
+        origin = [i for i, m in enumerate(ms) if m[0] == 0 and m[1] == CY0 * SIZE and m[2] == 0][0]
+        assert res[origin]["numVertices"] > 0, "CY0 does not name the surface chunk above the origin"
+    totV, totT, totS = int(view.totalVertices), int(view.totalTriangles), int(view.totalSeamNodes)
+
+    def pinned(n, dtype):
+        t = torch.empty(max(n, 1) * dtype.itemsize, dtype=torch.uint8, pin_memory=True)
+        return t, t.numpy().view(dtype)
+    keepV, hostV = pinned(totV + 1024, lc.MeshVertex)
+    keepT, hostT = pinned(totT + 1024, lc.MeshTriangle)
+    keepS, hostS = pinned(totS + 1024, lc.SeamNodeInfo)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed_region(step_fn, steps):
+        """K steps; L2 flushed before each; CUDA events on the launching stream around each step"""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record(stream)
+            step_fn()
+            b.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        return dev_ms, wall
+
+    def step_device():
+        rc, _, _ = ctx.generateBatchDevice(ms)
+        assert rc == 0
+
+    def step_e2e():
+        rc, _ = ctx.generateBatch(ms, hostV, hostT, hostS)
+        assert rc == 0
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    fp32_peak = lc.MeasureFP32Peak()
+
+    # ---- timed: device-resident ----
+    ctx.setProfiling(True)
+    ctx.getStats(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_ms, wall = timed_region(step_device, args.steps)
+    stats = ctx.getStats(reset=True)
+    ctx.setProfiling(False)
+    # ---- timed: end to end through the host-facing call ----
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, e2e_wall = timed_region(step_e2e, args.steps)
+    clocks = sampler.stop()
+
+    dev_ms_max = max_over_ranks(dev_ms)
+    e2e_ms_max = max_over_ranks(e2e_ms)
+    total_chunks = sum_over_ranks(nchunks) * args.steps
+    value = total_chunks / (dev_ms_max * 1e-3)
+    e2e_value = total_chunks / (e2e_ms_max * 1e-3)
+
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    E, Ey, N = stats["edges"] / K, stats["edgesY"] / K, stats["nodes"] / K
+    T, S, NE = stats["triangles"] / K, stats["seamNodes"] / K, stats["nonEmptyChunks"] / K
+    Q = T / 2
+    F3, F2 = (V + 2) ** 3, (V + 2) ** 2
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    stage_ms = {k: v / K for k, v in stats["ms"].items()}
+
+    # algorithmic work per launch, SURVEY.md 8(d)
+    herm_flop = (5 * Ey + 21 * (E - Ey)) * FLOP_PER_DENSITY + 60 * E
+    herm_tflops = herm_flop / (stage_ms["hermite"] * 1e-3) / 1e12 if stage_ms["hermite"] > 0 else 0.0
+    col_flop = nchunks * (F2 * FLOP_PER_DENSITY + 2 * F3)
+    classify_bytes = nchunks * 2 * F3 + 4 * E + 12 * N                 # S2 + S4
+    leaves_bytes = (8 * N + 20 * E + 32 * N) + (8 * N + 72 * N + 24 * Q) + (36 * N + 48 * N) + (4 * N + 36 * S + 48 * S)
+
+    def gbs(b, ms_):
+        return b / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+
+    prof = {}
+    ppath = os.path.join(ROOT, "profiles", "latest_traffic.json")
+    if os.path.exists(ppath):
+        try:
+            prof = json.load(open(ppath))
+        except Exception:
+            prof = {}
+
+    stages = [
+        {"stage": "columns (S1)", "bound": "fp32", "ms": stage_ms["columns"], "algorithmic_flop": col_flop,
+         "executed_flop": stats["terrainEvals"] / K * 0 + (stats["launches"]["columns"] > 0) * 0,
+         "achieved_tflops": col_flop / (stage_ms["columns"] * 1e-3) / 1e12 if stage_ms["columns"] > 0 else 0.0,
+         "peak_tflops": fp32_peak},
+        {"stage": "classify (S2+S4)", "bound": "hbm", "ms": stage_ms["classify"], "algorithmic_bytes": classify_bytes,
+         "achieved_gbs": gbs(classify_bytes, stage_ms["classify"]), "peak_gbs": hbm_peak},
+        {"stage": "hermite (S3)", "bound": "fp32", "ms": stage_ms["hermite"], "algorithmic_flop": herm_flop,
+         "achieved_tflops": herm_tflops, "peak_tflops": fp32_peak},
+        {"stage": "leaves (S5+S6+S8+S9+S10)", "bound": "hbm", "ms": stage_ms["leaves"], "algorithmic_bytes": leaves_bytes,
+         "achieved_gbs": gbs(leaves_bytes, stage_ms["leaves"]), "peak_gbs": hbm_peak},
+    ]
+    for s in stages:
+        s.pop("executed_flop", None)
+        if s["bound"] == "fp32":
+            s["frac"] = s["achieved_tflops"] / fp32_peak if fp32_peak else None
+        else:
+            s["frac"] = s["achieved_gbs"] / hbm_peak
+
+    h2d = nchunks * 16                                   # the caller's chunk list (4 ints per chunk)
+    d2h = totV * 48 + totT * 12 + totS * 48 + nchunks * 32   # mesh + seam arenas + per-chunk results
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world_size, "steps": K,
+        "warmup": args.warmup, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "chunks_per_gpu": nchunks, "non_empty_chunks_per_gpu": NE,
+                   "edges_per_step": E, "vertices_per_step": N, "triangles_per_step": T, "seam_nodes_per_step": S,
+                   "l2": "flushed before every timed step (256 MiB device memset, outside the step's events)",
+                   "timing": "CUDA events on the launching stream around each step, summed; max over ranks",
+                   "sharding": "one 512-chunk ring per GPU, no collective on the data path"},
+        "ms_per_step_wall_incl_flush": 1e3 * wall / K,
+        "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_max / K,
+                "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)"},
+        "gpu_launches": int(sum(stats["launches"].values())),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_hermite (FindEdgeIntersectionInfo)", "bound": "fp32",
+                     "achieved": herm_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": herm_tflops / fp32_peak if fp32_peak else None,
+                     "traffic": prof.get("hermite_dram_bytes_per_launch"),
+                     "algorithmic": "(5*E_y + 21*(E_x+E_z))*1217 + 60*E flop per launch (SURVEY.md 8d)",
+                     "peak_source": "measured in this run: independent FMA chains on all SMs (lvn_measure_fp32_peak); "
+                                    "nominal 74.4 TFLOP/s",
+                     "share_of_step": stage_ms["hermite"] / (dev_ms_max / K) if dev_ms_max else None},
+        "roofline_hbm": {"kernel": "k_leaves", "bound": "hbm", "achieved": stages[3]["achieved_gbs"], "peak": hbm_peak,
+                         "unit": "GB/s", "frac": stages[3]["frac"], "traffic": prof.get("leaves_dram_bytes_per_launch"),
+                         "peak_source": peak_src},
+        "stages": stages,
+    }
+
+    if world_size == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O      # the checker's CPU port, timed as the reported baseline
+        world = O.World(image=lc.Compute_GetNoiseImage(), default_material=0, voxels_per_chunk=V)
+        world.batch_counts(ms[:32])
+        t0 = time.perf_counter()
+        counts, threads = world.batch_counts(ms)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(counts[:, 0], res["numEdges"]) and np.array_equal(counts[:, 2], res["numTriangles"]), \
+            "CUDA path and oracle disagree on the bench workload"
+        line["cpu_baseline"] = {"value": nchunks / dt, "unit": "chunks/s", "cores": int(threads), "kind": "port",
+                                "sample": f"the full {nchunks}-chunk workload once ({dt:.1f} s), OpenMP over chunks; "
+                                          "oracle port of the reference pipeline (the OpenCL reference cannot run: no ICD)"}
+        world.close()
+    print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

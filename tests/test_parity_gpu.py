@@ -208,25 +208,33 @@ def test_batch_full_size_properties(lc, ctx, surface_cy):
     assert digest == digest2
 
 
-def test_octree_cache_semantics(lc, ctx, gpu_world, surface_cy):
+def test_octree_cache_semantics(lc, oracle_mod, surface_cy):
     """stale until freeChunkOctree (compute_octree.cpp:154-181,379-387), same as the oracle twin"""
-    mn = [256, surface_cy * 256, 256]
-    a = check_mesh(lc, ctx, gpu_world, mn)
-    yc = surface_cy * 64 + 32.5
-    ops = [lc.CSGOperationInfo.make(1, 1, 201, [84.5, yc, 84.5], [6, 6, 6]),
-           lc.CSGOperationInfo.make(0, 0, 3, [108.5, yc, 108.5], [5, 4, 3])]
-    import oracle.oracle as O
-    oops = [O.make_csg_op(1, 1, 201, [84.5, yc, 84.5], [6, 6, 6]), O.make_csg_op(0, 0, 3, [108.5, yc, 108.5], [5, 4, 3])]
-    assert ctx.applyCSGOperations(ops, mn, 256) == 0
-    gpu_world.apply_csg_operations(oops, mn, 256)
-    b = check_mesh(lc, ctx, gpu_world, mn)                 # both still serve the cached octree
-    assert b["numNodes"] == a["numNodes"]
-    ctx.freeChunkOctree(mn, 256)
-    gpu_world.free_chunk_octree(mn, 256)
-    c = check_mesh(lc, ctx, gpu_world, mn)                 # re-meshed from the edited field
-    assert c["numNodes"] != a["numNodes"]
-    ctx.freeChunkOctree(mn, 256)
-    gpu_world.free_chunk_octree(mn, 256)
+    ctx = lc.Compute_MeshGenContext.create(64)
+    world = oracle_mod.World(image=lc.Compute_GetNoiseImage(), default_material=0, voxels_per_chunk=64)
+    try:
+        mn = [0, surface_cy * 256, 0]
+        a = check_mesh(lc, ctx, world, mn)
+        assert a["numNodes"] > 0
+        yc = surface_cy * 64 + 32.5
+        specs = [(1, 1, 201, [20.5, yc, 20.5], [6, 6, 6]), (0, 0, 3, [44.5, yc, 44.5], [5, 4, 3])]
+        assert ctx.applyCSGOperations([lc.CSGOperationInfo.make(*s) for s in specs], mn, 256) == 0
+        world.apply_csg_operations([oracle_mod.make_csg_op(*s) for s in specs], mn, 256)
+        b = check_mesh(lc, ctx, world, mn)                 # both still serve the cached octree
+        assert b["numNodes"] == a["numNodes"]
+        ctx.freeChunkOctree(mn, 256)
+        world.free_chunk_octree(mn, 256)
+        c = check_mesh(lc, ctx, world, mn)                 # re-meshed from the edited field
+        assert c["numNodes"] != a["numNodes"]
+        # a chunk that was empty is not cached at all: an edit shows up without freeChunkOctree
+        em = [0, 15 * 256, 0]
+        assert check_mesh(lc, ctx, world, em)["numNodes"] == 0
+        blob = (0, 1, 2, [30.5, 15 * 64 + 30.5, 30.5], [8, 8, 8])
+        assert ctx.applyCSGOperations([lc.CSGOperationInfo.make(*blob)], em, 256) == 0
+        world.apply_csg_operations([oracle_mod.make_csg_op(*blob)], em, 256)
+        assert check_mesh(lc, ctx, world, em)["numNodes"] > 0
+    finally:
+        ctx.destroy(); world.close()
 
 
 def compare_csg_field(ctx, world, mn, size=256):
@@ -413,5 +421,6 @@ def test_gpu_scan_compact(lc, oracle_mod):
         assert total == int(data.sum())
         assert np.array_equal(scan, np.cumsum(data) - data)
         vals = rng.randint(0, 1 << 30, size=n).astype(np.int32)
-        assert np.array_equal(lc.CompactIndexArray(vals, data), vals[data != 0])
+        valid = (data != 0).astype(np.int32)          # validity flags are 0 / 1 (compact.cl:4-16)
+        assert np.array_equal(lc.CompactIndexArray(vals, valid), vals[valid != 0])
     assert lc.ExclusiveScan(np.zeros(0, np.int32))[0] == 0
