@@ -77,8 +77,9 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.5)      # let nvidia-smi attach before the timed region starts
         except Exception:
             self.proc = None
 
@@ -97,9 +98,12 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                clk, cmax, pw = float(f[1]), float(f[2]), float(f[3])
             except ValueError:
                 continue
+            if pw < 250.0:          # idle sample taken before / after the kernels ran
+                continue
+            sm.append(clk); mx.append(cmax)
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
@@ -142,7 +146,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,6 +285,7 @@ def main():
     herm_flop = (5 * Ey + 21 * (E - Ey)) * FLOP_PER_DENSITY + 60 * E
     herm_tflops = herm_flop / (stage_ms["hermite"] * 1e-3) / 1e12 if stage_ms["hermite"] > 0 else 0.0
     col_flop = nchunks * (F2 * FLOP_PER_DENSITY + 2 * F3)
+    col_sets = len({(int(m[0]), int(m[2])) for m in ms})
     classify_bytes = nchunks * 2 * F3 + 4 * E + 12 * N                 # S2 + S4
     leaves_bytes = (8 * N + 20 * E + 32 * N) + (8 * N + 72 * N + 24 * Q) + (36 * N + 48 * N) + (4 * N + 36 * S + 48 * S)
 
@@ -296,9 +301,12 @@ def main():
             prof = {}
 
     stages = [
+        # chunks of one vertical stack share a column set: the kernel executes colsets*F^2 Terrain
+        # evaluations, not chunks*F^2; the fraction is taken on the EXECUTED flops
         {"stage": "columns (S1)", "bound": "fp32", "ms": stage_ms["columns"], "algorithmic_flop": col_flop,
-         "executed_flop": stats["terrainEvals"] / K * 0 + (stats["launches"]["columns"] > 0) * 0,
-         "achieved_tflops": col_flop / (stage_ms["columns"] * 1e-3) / 1e12 if stage_ms["columns"] > 0 else 0.0,
+         "executed_flop": col_sets * F2 * FLOP_PER_DENSITY,
+         "achieved_tflops": col_sets * F2 * FLOP_PER_DENSITY / (stage_ms["columns"] * 1e-3) / 1e12
+         if stage_ms["columns"] > 0 else 0.0,
          "peak_tflops": fp32_peak},
         {"stage": "classify (S2+S4)", "bound": "hbm", "ms": stage_ms["classify"], "algorithmic_bytes": classify_bytes,
          "achieved_gbs": gbs(classify_bytes, stage_ms["classify"]), "peak_gbs": hbm_peak},
@@ -308,7 +316,6 @@ def main():
          "achieved_gbs": gbs(leaves_bytes, stage_ms["leaves"]), "peak_gbs": hbm_peak},
     ]
     for s in stages:
-        s.pop("executed_flop", None)
         if s["bound"] == "fp32":
             s["frac"] = s["achieved_tflops"] / fp32_peak if fp32_peak else None
         else:
