@@ -206,19 +206,23 @@ static float unorm_grad(uint8_t b)
 
 static int upload_noise_image()
 {
-    std::vector<float2> g2(65536);
+    std::vector<float2> g2(257 * 257);   // + one wrapped column and row (density.cuh: LVN_G2PITCH)
     std::vector<float4> g3(65536);
+    for (int r = 0; r < 257; r++)
+        for (int c = 0; c < 257; c++) {
+            const uint8_t *px = &g.image[(size_t)(((r & 255) << 8) | (c & 255)) * 4];
+            g2[(size_t)r * 257 + c] = make_float2(unorm_grad(px[0]), unorm_grad(px[1]));
+        }
     for (int t = 0; t < 65536; t++) {
         const uint8_t *px = &g.image[(size_t)t * 4];
-        g2[t] = make_float2(unorm_grad(px[0]), unorm_grad(px[1]));
         // snoise3's second lookup uses the UNORM alpha v/255 as an un-centred x coordinate:
         // NEAREST + REPEAT lands on column v, and on column 0 for v = 255 (simplex.cl:184-185)
         const int col = px[3] == 255 ? 0 : (int)px[3];
         g3[t] = make_float4(unorm_grad(px[0]), unorm_grad(px[1]), unorm_grad(px[2]), int_as_float_host(col));
     }
-    if (!g.d_grad2) CU(cudaMalloc((void **)&g.d_grad2, 65536 * sizeof(float2)));
+    if (!g.d_grad2) CU(cudaMalloc((void **)&g.d_grad2, g2.size() * sizeof(float2)));
     if (!g.d_grad3) CU(cudaMalloc((void **)&g.d_grad3, 65536 * sizeof(float4)));
-    CU(cudaMemcpy(g.d_grad2, g2.data(), 65536 * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g.d_grad2, g2.data(), g2.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_grad3, g3.data(), 65536 * sizeof(float4), cudaMemcpyHostToDevice));
     return LVN_SUCCESS;
 }

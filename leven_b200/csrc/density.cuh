@@ -22,10 +22,13 @@ namespace lvn {
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
+// snoise2's gradient table is 257 x 257 (row pitch LVN_G2PITCH): texel (col, row) of the 256 x 256
+// REPEAT image plus one wrapped column and row, so the "+1" corners need no second wrap.
+#define LVN_G2PITCH 257
+
 // One simplex corner: t = 0.5 - |P|^2; n = t < 0 ? 0 : t^4 * dot(grad, P)
-__device__ __forceinline__ float corner2(const float2 *__restrict__ grad, int ii, int jj, float x, float y)
+__device__ __forceinline__ float corner2(const float2 g, float x, float y)
 {
-    const float2 g = __ldg(&grad[((jj & 255) << 8) | (ii & 255)]);
     const float t0 = 0.5f - __fmaf_rn(y, y, x * x);
     const float d = __fmaf_rn(g.y, y, g.x * x);
     const float t = t0 * t0;
@@ -39,14 +42,15 @@ __device__ __forceinline__ float snoise2(const float2 *__restrict__ grad, float 
     const float ix = floorf(px + s), iy = floorf(py + s);
     const float t = (ix + iy) * LVN_G2;
     const float x0 = px - (ix - t), y0 = py - (iy - t);
-    const int ii = __float2int_rz(ix), jj = __float2int_rz(iy);
+    const int ii = __float2int_rz(ix) & 255, jj = __float2int_rz(iy) & 255;
     const bool xy = x0 > y0;
     const float o1x = xy ? 1.f : 0.f, o1y = xy ? 0.f : 1.f;
-    const int i1 = xy ? 1 : 0, j1 = xy ? 0 : 1;
+    const float2 *g = grad + (jj * LVN_G2PITCH + ii);
+    const float2 g0 = __ldg(g), g1 = __ldg(g + (xy ? 1 : LVN_G2PITCH)), g2 = __ldg(g + (LVN_G2PITCH + 1));
 
-    const float n0 = corner2(grad, ii, jj, x0, y0);
-    const float n1 = corner2(grad, ii + i1, jj + j1, x0 - o1x + LVN_G2, y0 - o1y + LVN_G2);
-    const float n2 = corner2(grad, ii + 1, jj + 1, x0 - (1.f - 2.f * LVN_G2), y0 - (1.f - 2.f * LVN_G2));
+    const float n0 = corner2(g0, x0, y0);
+    const float n1 = corner2(g1, x0 - o1x + LVN_G2, y0 - o1y + LVN_G2);
+    const float n2 = corner2(g2, x0 - (1.f - 2.f * LVN_G2), y0 - (1.f - 2.f * LVN_G2));
     return 70.f * (n0 + n1 + n2);
 }
 

@@ -68,7 +68,7 @@ struct ChunkScratch {
 };
 
 struct DensityParams {
-    const float2 *grad2;      // [256*256] snoise2 gradients (texel.xy * 4 - 1)
+    const float2 *grad2;      // [257*257] snoise2 gradients (texel.xy * 4 - 1), wrap-padded
     const float4 *grad3;      // [256*256] snoise3 gradients xyz, w = bits of the perm column
     int kind;                 // 0 terrain, 1 stress
     float param;              // stress threshold

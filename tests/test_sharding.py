@@ -1,0 +1,71 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the round-robin sharding and the count
+gather.  The per-chunk work is done by the oracle here (no GPU in this suite);
+the GPU suite checks that the CUDA path gives the same per-chunk counts."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, SEED
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, chunks, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from leven_b200 import sharding
+    from oracle import oracle as O
+    mine = sharding.shard_round_robin(len(chunks), rank, world_size)
+    world = O.World(seed=SEED)
+    counts, _ = world.batch_counts(chunks[mine])
+    local = np.stack([np.where(counts[:, 2] > 0, counts[:, 1], 0), counts[:, 2], counts[:, 3]], axis=1)
+    c, off, tot = sharding.gather_global_offsets(local, mine, len(chunks))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), counts=c, offsets=off, totals=tot, mine=mine)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_round_robin_partition():
+    from leven_b200 import sharding
+    for world in (1, 2, 4, 8):
+        parts = [sharding.shard_round_robin(4096, r, world) for r in range(world)]
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(4096))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    sw = sharding.sweep_chunks()
+    assert len(sw) == 4096 and sw[:, 0].min() == -8 * 256 and sw[:, 0].max() == 7 * 256 and sw[:, 1].max() == 15 * 256
+    owners = [sharding.stable_owner(c[:3], 256, 8) for c in sw[:512]]
+    assert set(owners) == set(range(8))
+    assert owners == [sharding.stable_owner(c[:3], 256, 8) for c in sw[:512]]
+
+
+def test_world_size_2_gloo_count_gather(tmp_path, built, surface_cy):
+    from leven_b200 import sharding
+    from oracle import oracle as O
+    chunks = np.array([[cx * 256, (surface_cy + dy) * 256, 0, 256] for dy in (-1, 0) for cx in range(-2, 2)], np.int32)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, chunks, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["counts"], r1["counts"]) and np.array_equal(r0["offsets"], r1["offsets"])
+    assert set(r0["mine"]).isdisjoint(set(r1["mine"])) and len(r0["mine"]) + len(r1["mine"]) == len(chunks)
+    # single-process answer
+    world = O.World(seed=SEED)
+    counts, _ = world.batch_counts(chunks)
+    ref = np.stack([np.where(counts[:, 2] > 0, counts[:, 1], 0), counts[:, 2], counts[:, 3]], axis=1)
+    assert np.array_equal(r0["counts"], ref)
+    assert np.array_equal(r0["offsets"], np.cumsum(ref, axis=0) - ref)
+    assert np.array_equal(r0["totals"], ref.sum(axis=0)) and ref.sum() > 0
