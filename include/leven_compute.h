@@ -128,7 +128,9 @@ int lvn_meshgen_generate_chunk_mesh(lvn_meshgen *ctx, const int32_t min[3], int 
 
 typedef struct lvn_chunk_result {
     int32_t numEdges, numVertices, numTriangles, numSeamNodes;
-    int32_t vertexOffset, triangleOffset, seamOffset;   /* element offsets into the arenas */
+    int32_t vertexOffset, triangleOffset, seamOffset;   /* element offsets into the arenas (the
+                                                          * slices of different chunks never overlap;
+                                                          * the device arenas may have gaps) */
     int32_t status;                                     /* 0 or a negative LVN_* code */
 } lvn_chunk_result;
 
@@ -199,6 +201,11 @@ typedef struct lvn_stage_stats {
 int lvn_meshgen_set_profiling(lvn_meshgen *ctx, int enabled);   /* per-stage events on/off */
 /* launch on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the context's own) */
 int lvn_meshgen_set_stream(lvn_meshgen *ctx, void *cudaStream);
+/* A batch is cut into `lanes` independent slices (0 = chosen from the batch size) whose kernel
+ * chains run on `streams` (1..4) CUDA streams forked from and joined back to the context's
+ * stream; the host-path batch call drains finished lanes over the copy engine meanwhile. */
+int lvn_meshgen_set_pipeline(lvn_meshgen *ctx, int lanes, int streams);
+int lvn_meshgen_get_pipeline(const lvn_meshgen *ctx, int *lanesOfLastBatch, int *streamsOfLastBatch);
 /* FP32 roofline denominator: independent FMA chains on every SM, CUDA-event timed (2 flop/FMA) */
 int lvn_measure_fp32_peak(double *tflops);
 int lvn_meshgen_get_stats(lvn_meshgen *ctx, lvn_stage_stats *out, int reset);

@@ -114,6 +114,8 @@ ABI = {
     "lvn_meshgen_set_profiling": (_I, [_P, _I]),
     "lvn_meshgen_get_stats": (_I, [_P, _P, _I]),
     "lvn_meshgen_set_stream": (_I, [_P, _P]),
+    "lvn_meshgen_set_pipeline": (_I, [_P, _I, _I]),
+    "lvn_meshgen_get_pipeline": (_I, [_P, _P, _P]),
     "lvn_measure_fp32_peak": (_I, [_P]),
     "lvn_find_next_prime": (_I, [_I]),
     "lvn_exclusive_scan": (_I, [_P, _P, _I]),
@@ -344,6 +346,16 @@ class Compute_MeshGenContext:
         for k in ("nodeCodes", "nodeEdgeMasks", "nodeMaterials", "nodeQEFs", "nodePositions", "nodeNormals"):
             out[k] = bufs[k][:N].copy()
         return out
+
+    def setPipeline(self, lanes, streams):
+        """lanes (0 = automatic) x streams of a batch call, see lvn_meshgen_set_pipeline"""
+        return self._L.lvn_meshgen_set_pipeline(self.privateCtx_, int(lanes), int(streams))
+
+    def getPipeline(self):
+        """(lanes of the last batch, configured streams)"""
+        a, b = C.c_int(0), C.c_int(0)
+        self._L.lvn_meshgen_get_pipeline(self.privateCtx_, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def setStream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None"""

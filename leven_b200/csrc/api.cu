@@ -11,6 +11,7 @@
 // blocking reads per chunk).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -90,9 +91,15 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        CU(cudaMallocHost((void **)&p, n * sizeof(T)));
+        // mapped: kernels may write results straight into it (zero-copy), no copy-engine transfer
+        CU(cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocMapped));
         cap = n;
         return 0;
+    }
+    T *dev() const   // the device-side address of the mapping
+    {
+        T *d = nullptr;
+        return (p && cudaHostGetDevicePointer((void **)&d, p, 0) == cudaSuccess) ? d : nullptr;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
@@ -354,6 +361,9 @@ struct OctreeEntry {
     }
 };
 
+constexpr int LVN_MAX_LANES = 32;
+constexpr int LVN_MAX_STREAMS = 4;
+
 struct lvn_meshgen {
     Dims dims;
     cudaStream_t stream = nullptr;      // where the kernels go (own stream or the caller's)
@@ -373,7 +383,10 @@ struct lvn_meshgen {
     DevBuf<lvn_mesh_vertex> d_vertices;
     DevBuf<int> d_tris;
     DevBuf<lvn_seam_node_info> d_seams;
-    DevBuf<ArenaCounters> d_counters;
+    DevBuf<uint4> d_slab;
+    DevBuf<unsigned int> d_slabEy, d_ticket;
+    DevBuf<int> d_colMin, d_colMax;            // per column set: ordered-int keys of the height range
+    DevBuf<TileRef> d_edgeTiles, d_nodeTiles;  // tile directories, one slice per lane
     DevBuf<uint8_t> d_tmpFields;
     DevBuf<uint8_t *> d_fieldPtrs;
     // debug stage outputs
@@ -388,11 +401,32 @@ struct lvn_meshgen {
     PinBuf<ChunkDesc> h_descs;
     PinBuf<ChunkHdr> h_hdrs;
     PinBuf<int4> h_colOrigins;
-    PinBuf<ArenaCounters> h_counters;
     PinBuf<unsigned int> h_small;
 
-    ArenaCounters lastCounters = {};
+    ArenaCounters lastCounters = {};   // totals over the lanes of the last batch
     int lastN = 0;
+
+    // lanes of a batch (run_batch): independent slices of the chunk list, each a chain
+    // classify -> hermite -> leaves on one of `numStreams` streams, so that the tail of one
+    // lane's kernel overlaps the next lane's work and (host path) the copy engine drains lane k
+    // while lane k+1 computes
+    int cfgLanes = 0;                  // 0 = chosen per call (choose_pipeline)
+    int cfgStreams = 2;
+    int numStreams = 1;                // of the last batch
+    cudaStream_t laneStreams[LVN_MAX_STREAMS] = {nullptr};   // [0] unused: the context's stream
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evFork = nullptr, evCopy = nullptr;
+    cudaEvent_t evLane[LVN_MAX_LANES] = {nullptr};
+    cudaEvent_t evJoin[LVN_MAX_STREAMS] = {nullptr};
+    int numLanes = 0;
+    int laneFirst[LVN_MAX_LANES + 1] = {0};      // lane k owns internal chunks [laneFirst[k], laneFirst[k+1])
+    ArenaCaps laneBase[LVN_MAX_LANES] = {};      // where lane k's slice of every arena starts
+    ArenaCounters laneCounters[LVN_MAX_LANES] = {};
+    int64_t hostBase[LVN_MAX_LANES][3] = {};     // vertices, triangles, seam nodes: lane k's place in the host arenas
+    bool hostLayout = false;                     // results address the caller's host arenas
+    std::vector<int> perm;                       // internal (lane-major) chunk order -> caller's index
+    bool trace = false;                          // LVN_TRACE=1: per-lane kernel timeline on stderr
+    std::vector<cudaEvent_t> traceEv, traceCopyEv;
 
     bool profiling = false;
     cudaEvent_t ev[2 * LVN_NUM_STAGES] = {nullptr};
@@ -419,6 +453,15 @@ extern "C" lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk)
     if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->stream = ctx->ownStream;
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 1; i < LVN_MAX_STREAMS; i++) cudaStreamCreateWithFlags(&ctx->laneStreams[i], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming);
+    for (int i = 0; i < LVN_MAX_LANES; i++) cudaEventCreateWithFlags(&ctx->evLane[i], cudaEventDisableTiming);
+    for (int i = 0; i < LVN_MAX_STREAMS; i++) cudaEventCreateWithFlags(&ctx->evJoin[i], cudaEventDisableTiming);
+    if (const char *e = getenv("LVN_LANES")) ctx->cfgLanes = atoi(e);
+    if (const char *e = getenv("LVN_STREAMS")) ctx->cfgStreams = atoi(e);
+    if (const char *e = getenv("LVN_TRACE")) ctx->trace = atoi(e) != 0;
     return ctx;
 }
 
@@ -431,14 +474,22 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_colOrigins.release(); ctx->d_heights.release();
     ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
     ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release();
-    ctx->d_vertices.release(); ctx->d_tris.release(); ctx->d_seams.release(); ctx->d_counters.release();
+    ctx->d_vertices.release(); ctx->d_tris.release(); ctx->d_seams.release();
+    ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release();
     ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
+    ctx->d_colMin.release(); ctx->d_colMax.release(); ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
     ctx->d_ops.release();
-    ctx->h_descs.release(); ctx->h_hdrs.release(); ctx->h_colOrigins.release(); ctx->h_counters.release();
+    ctx->h_descs.release(); ctx->h_hdrs.release(); ctx->h_colOrigins.release();
     ctx->h_small.release();
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 1; i < LVN_MAX_STREAMS; i++) if (ctx->laneStreams[i]) cudaStreamDestroy(ctx->laneStreams[i]);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
+    for (int i = 0; i < LVN_MAX_LANES; i++) if (ctx->evLane[i]) cudaEventDestroy(ctx->evLane[i]);
+    for (int i = 0; i < LVN_MAX_STREAMS; i++) if (ctx->evJoin[i]) cudaEventDestroy(ctx->evJoin[i]);
     cudaStreamDestroy(ctx->ownStream);
     delete ctx;
 }
@@ -457,6 +508,22 @@ extern "C" int lvn_meshgen_set_stream(lvn_meshgen *ctx, void *cudaStream)
     if (!ctx) return LVN_ERR_INVALID_VALUE;
     cudaStreamSynchronize(ctx->stream);
     ctx->stream = cudaStream ? (cudaStream_t)cudaStream : ctx->ownStream;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_set_pipeline(lvn_meshgen *ctx, int lanes, int streams)
+{
+    if (!ctx || lanes < 0 || lanes > LVN_MAX_LANES || streams < 1 || streams > LVN_MAX_STREAMS) return LVN_ERR_INVALID_VALUE;
+    ctx->cfgLanes = lanes;
+    ctx->cfgStreams = streams;
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_get_pipeline(const lvn_meshgen *ctx, int *lanesOfLastBatch, int *streams)
+{
+    if (!ctx) return LVN_ERR_INVALID_VALUE;
+    if (lanesOfLastBatch) *lanesOfLastBatch = ctx->numLanes;
+    if (streams) *streams = ctx->numStreams;
     return LVN_SUCCESS;
 }
 
@@ -544,6 +611,15 @@ struct BatchOpts {
     bool ignoreFieldCache = false;
 };
 
+struct HostOut {   // caller-owned destination of lvn_meshgen_generate_batch
+    lvn_mesh_vertex *vertices;
+    int64_t vertexCapacity;
+    lvn_mesh_triangle *triangles;
+    int64_t triangleCapacity;
+    lvn_seam_node_info *seams;
+    int64_t seamCapacity;
+};
+
 static int fill_desc(lvn_meshgen *ctx, const int32_t *ms, ChunkDesc &cd)
 {
     const Dims &d = ctx->dims;
@@ -560,7 +636,45 @@ static int fill_desc(lvn_meshgen *ctx, const int32_t *ms, ChunkDesc &cd)
     return LVN_SUCCESS;
 }
 
-static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const BatchOpts &opts)
+// Lanes x streams of a batch.  Measured on B200 (profiles/r01_pipeline.md): every kernel
+// boundary costs ~30 us extra while a bulk device-to-host copy is in flight, and a lane has
+// ~40 us of launch gaps and kernel tails, so few lanes win: the device-resident pass runs two
+// lanes on two streams (the tail of one kernel overlaps the other lane), the host pass four
+// lanes on one stream (lane k is copied out while lanes k+1.. compute).
+static void choose_pipeline(const lvn_meshgen *ctx, int n, const BatchOpts &opts, bool hostPath, int &lanes, int &streams)
+{
+    lanes = ctx->cfgLanes;
+    streams = ctx->cfgStreams;
+    if (lanes <= 0) {
+        lanes = n >= 128 ? (hostPath ? 4 : 2) : 1;
+        streams = hostPath ? 1 : 2;
+    }
+    // per-stage event timing and the stage dumps want one kernel at a time on one stream
+    if (ctx->profiling || opts.debug) lanes = 1;
+    lanes = std::max(1, std::min(std::min(lanes, LVN_MAX_LANES), n));
+    streams = lanes == 1 ? 1 : std::max(1, std::min(std::min(streams, LVN_MAX_STREAMS), lanes));
+}
+
+// every stream a lane ran on, and the copy stream, rejoin the context's stream
+static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies)
+{
+    for (int r = 1; r < numStreams; r++) {
+        CU(cudaEventRecord(ctx->evJoin[r], ctx->laneStreams[r]));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[r], 0));
+    }
+    if (copies) {
+        CU(cudaEventRecord(ctx->evCopy, ctx->copyStream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evCopy, 0));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LVN_SUCCESS;
+}
+
+// One pass of the path over n chunks.  Results stay in the context's arenas; with `out` the
+// mesh / seam arenas of every lane are also copied into the caller's host arenas while the
+// following lanes are still computing.
+static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const BatchOpts &opts,
+                     const HostOut *out = nullptr)
 {
     if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
     if (!ctx || n < 0 || (n > 0 && !chunkMinSize)) return LVN_ERR_INVALID_VALUE;
@@ -568,21 +682,39 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     const size_t FF = (size_t)d.F * d.F, HH = (size_t)d.H * d.H, VV = (size_t)d.V * d.V, F3 = FF * d.F;
     cudaStream_t st = ctx->stream;
     ctx->lastN = n;
+    ctx->numLanes = 0;
+    ctx->hostLayout = false;
     memset(&ctx->lastCounters, 0, sizeof(ctx->lastCounters));
     if (n == 0) return LVN_SUCCESS;
 
-    // ---- descriptors, column-set dedupe, cached fields ----
+    // ---- lanes: lane k takes the caller's chunks k, k + S, k + 2S, ... (neighbouring chunks of a
+    //      clipmap ring or a sweep do similar work, so strided lanes are balanced) ----
+    int S = 1, R = 1;
+    choose_pipeline(ctx, n, opts, out != nullptr, S, R);
+    ctx->numLanes = S;
+    ctx->numStreams = R;
+    ctx->perm.resize(n);
+    {
+        int p = 0;
+        for (int k = 0; k < S; k++) {
+            ctx->laneFirst[k] = p;
+            for (int i = k; i < n; i += S) ctx->perm[p++] = i;
+        }
+        ctx->laneFirst[S] = p;
+    }
+
+    // ---- descriptors (internal, lane-major order), column-set dedupe, cached fields ----
     LV(ctx->h_descs.reserve(n));
     LV(ctx->h_colOrigins.reserve(n));
-    LV(ctx->h_hdrs.reserve(n));
-    LV(ctx->h_counters.reserve(1));
+    LV(ctx->h_hdrs.reserve(n + S));
     std::map<std::tuple<int, int, int>, int> colSets;
     int numColSets = 0, numTmpFields = 0;
     std::vector<int> tmpFieldChunk;
-    for (int i = 0; i < n; i++) {
-        ChunkDesc &cd = ctx->h_descs.p[i];
-        LV(fill_desc(ctx, &chunkMinSize[4 * i], cd));
-        auto it = opts.ignoreFieldCache ? ctx->fields.end() : ctx->fields.find(make_key(&chunkMinSize[4 * i], cd.size));
+    for (int p = 0; p < n; p++) {
+        const int32_t *ms = &chunkMinSize[4 * ctx->perm[p]];
+        ChunkDesc &cd = ctx->h_descs.p[p];
+        LV(fill_desc(ctx, ms, cd));
+        auto it = opts.ignoreFieldCache ? ctx->fields.end() : ctx->fields.find(make_key(ms, cd.size));
         if (it != ctx->fields.end()) {
             const FieldEntry &fe = it->second;
             cd.source = SRC_FIELD;
@@ -607,23 +739,30 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         } else {
             cd.source = SRC_FIELD;
             cd.edgeMode = EDGES_FRESH;
-            tmpFieldChunk.push_back(i);
+            tmpFieldChunk.push_back(p);
             numTmpFields++;
         }
     }
 
     // ---- workspace ----
     LV(ctx->d_descs.reserve(n));
-    LV(ctx->d_hdrs.reserve(n));
+    LV(ctx->d_hdrs.reserve(n + S));
     LV(ctx->d_colOrigins.reserve(std::max(numColSets, 1)));
     LV(ctx->d_heights.reserve(std::max<size_t>((size_t)numColSets * FF, 1)));
+    LV(ctx->d_colMin.reserve(std::max(numColSets, 1)));
+    LV(ctx->d_colMax.reserve(std::max(numColSets, 1)));
     LV(ctx->d_bitsLo.reserve(n * FF));
     LV(ctx->d_bitsHi.reserve(n * FF));
     LV(ctx->d_rowE.reserve(n * HH));
     LV(ctx->d_rowN.reserve(n * VV));
     LV(ctx->d_rowQ.reserve(n * VV));
     LV(ctx->d_rowS.reserve(n * VV));
-    LV(ctx->d_counters.reserve(1));
+    LV(ctx->d_slab.reserve((size_t)n * LVN_MAX_SLABS));
+    LV(ctx->d_slabEy.reserve((size_t)n * LVN_MAX_SLABS));
+    if ((size_t)n > ctx->d_ticket.cap) {
+        LV(ctx->d_ticket.reserve(n));
+        CU(cudaMemsetAsync(ctx->d_ticket.p, 0, ctx->d_ticket.cap * sizeof(unsigned int), st));   // k_rows leaves it zero
+    }
     if (numTmpFields) {
         LV(ctx->d_tmpFields.reserve((size_t)numTmpFields * F3));
         for (int k = 0; k < numTmpFields; k++)
@@ -644,10 +783,14 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     ChunkScratch ws;
     ws.bitsLo = ctx->d_bitsLo.p; ws.bitsHi = ctx->d_bitsHi.p;
     ws.rowE = ctx->d_rowE.p; ws.rowN = ctx->d_rowN.p; ws.rowQ = ctx->d_rowQ.p; ws.rowS = ctx->d_rowS.p;
+    ws.slab = ctx->d_slab.p; ws.slabEy = ctx->d_slabEy.p; ws.ticket = ctx->d_ticket.p;
 
+    // ---- S1 for the whole batch: the column sets are shared between the lanes ----
     if (numColSets) {
+        CU(cudaMemsetAsync(ctx->d_colMin.p, 0x7f, numColSets * sizeof(int), st));   // ordered key of +3.4e38
+        CU(cudaMemsetAsync(ctx->d_colMax.p, 0x80, numColSets * sizeof(int), st));   // ordered key of -3.4e38
         StageTimer t(ctx, LVN_STAGE_COLUMNS, 1);
-        launch_columns(dp, d, ctx->d_colOrigins.p, numColSets, ctx->d_heights.p, st);
+        launch_columns(dp, d, ctx->d_colOrigins.p, numColSets, ctx->d_heights.p, ctx->d_colMin.p, ctx->d_colMax.p, st);
         ctx->stats.terrainEvals += (int64_t)numColSets * (int64_t)FF;
     }
     if (numTmpFields) {
@@ -656,7 +799,6 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         std::vector<ChunkDesc> sub(numTmpFields);
         std::vector<uint8_t *> subPtrs(numTmpFields);
         for (int k = 0; k < numTmpFields; k++) { sub[k] = ctx->h_descs.p[tmpFieldChunk[k]]; subPtrs[k] = (uint8_t *)sub[k].field; }
-        // reuse the tail of d_descs / d_fieldPtrs: upload compact arrays
         DevBuf<ChunkDesc> dsub; DevBuf<uint8_t *> dptr;
         LV(dsub.reserve(numTmpFields)); LV(dptr.reserve(numTmpFields));
         CU(cudaMemcpyAsync(dsub.p, sub.data(), numTmpFields * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
@@ -666,80 +808,196 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         dsub.release(); dptr.release();
     }
 
+    // Header array: lane k's chunk headers, then one slot holding the lane's ArenaCounters.
+    // Kernels of lane k index it with the chunk's internal index through a pointer advanced by k
+    // slots.  The host's copy is a mapped pinned mirror that the kernels write directly (k_rows
+    // the headers, k_leaves the final counters): a small copy-engine transfer at the end of a
+    // lane would queue behind the bulk mesh copies of the lanes before it.
+    static_assert(sizeof(ArenaCounters) <= sizeof(ChunkHdr), "the counters live in a header slot");
+    ChunkHdr *h_hdrs_dev = ctx->h_hdrs.dev();
+    if (!h_hdrs_dev) { g_lastCudaError = "pinned header mirror is not mapped"; return LVN_ERR_CUDA; }
+    auto lane_counters_dev = [&](int k) { return (ArenaCounters *)(ctx->d_hdrs.p + ctx->laneFirst[k + 1] + k); };
+    auto lane_counters_host = [&](int k) { return (const ArenaCounters *)(ctx->h_hdrs.p + ctx->laneFirst[k + 1] + k); };
+
     for (int attempt = 0; attempt < 3; attempt++) {
         if (opts.debug) {
             LV(ctx->d_dbgCodes.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgMasks.reserve(ctx->d_vertices.cap));
             LV(ctx->d_dbgMats.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgQefs.reserve(ctx->d_vertices.cap * 16));
             LV(ctx->d_dbgPos.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgNrm.reserve(ctx->d_vertices.cap));
         }
+        // every lane owns an equal slice of every arena and of the tile directories
         ArenaCaps caps;
-        caps.edges = (unsigned int)std::min<size_t>(ctx->d_edgeKeys.cap, 0xffffffffu);
-        caps.nodes = (unsigned int)std::min<size_t>(ctx->d_vertices.cap, 0xffffffffu);
-        caps.quads = (unsigned int)std::min<size_t>(ctx->d_tris.cap / 6, 0xffffffffu);
-        caps.seams = (unsigned int)std::min<size_t>(ctx->d_seams.cap, 0xffffffffu);
-        CU(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ArenaCounters), st));
-        {
-            StageTimer t(ctx, LVN_STAGE_CLASSIFY, 1);
-            launch_classify(d, ctx->d_descs.p, n, ctx->d_heights.p, ctx->d_hdrs.p, ws, ctx->d_counters.p, caps,
-                            ctx->d_edgeKeys.p, st);
+        caps.edges = (unsigned int)std::min<size_t>(ctx->d_edgeKeys.cap / S, 0x7fffffffu);
+        caps.nodes = (unsigned int)std::min<size_t>(ctx->d_vertices.cap / S, 0x7fffffffu);
+        caps.quads = (unsigned int)std::min<size_t>(ctx->d_tris.cap / 6 / S, 0x7fffffffu);
+        caps.seams = (unsigned int)std::min<size_t>(ctx->d_seams.cap / S, 0x7fffffffu);
+        const int maxLaneChunks = ctx->laneFirst[1] - ctx->laneFirst[0];
+        const unsigned int tileCap = std::max(caps.edges, caps.nodes) / LVN_TILE + (unsigned int)maxLaneChunks + 1u;
+        LV(ctx->d_edgeTiles.reserve((size_t)tileCap * S));
+        LV(ctx->d_nodeTiles.reserve((size_t)tileCap * S));
+        CU(cudaMemsetAsync(ctx->d_hdrs.p, 0, (size_t)(n + S) * sizeof(ChunkHdr), st));   // zero counters
+        if (R > 1) {
+            CU(cudaEventRecord(ctx->evFork, st));
+            for (int r = 1; r < R; r++) CU(cudaStreamWaitEvent(ctx->laneStreams[r], ctx->evFork, 0));
         }
-        {
-            StageTimer t(ctx, LVN_STAGE_HERMITE, 1);
-            launch_hermite(dp, d, ctx->d_descs.p, n, ctx->d_hdrs.p, ctx->d_heights.p, ctx->d_edgeKeys.p,
-                           ctx->d_edgeInfo.p, st);
+        if (ctx->trace) {
+            while (ctx->traceEv.size() < (size_t)(1 + 5 * S)) { cudaEvent_t e; cudaEventCreate(&e); ctx->traceEv.push_back(e); }
+            cudaEventRecord(ctx->traceEv[0], st);
         }
-        {
-            StageTimer t(ctx, LVN_STAGE_LEAVES, 1);
-            NodeDebug dbg = {};
-            if (opts.debug) {
-                dbg.codes = ctx->d_dbgCodes.p; dbg.edgeMasks = ctx->d_dbgMasks.p; dbg.matWords = ctx->d_dbgMats.p;
-                dbg.qefs = ctx->d_dbgQefs.p; dbg.positions = ctx->d_dbgPos.p; dbg.normals = ctx->d_dbgNrm.p;
+#define LVN_TRACE_EV(i) do { if (ctx->trace) cudaEventRecord(ctx->traceEv[1 + 5 * k + (i)], ls); } while (0)
+        auto enqueue_lane = [&](int k) -> int {
+            cudaStream_t ls = (k % R) == 0 ? st : ctx->laneStreams[k % R];
+            const int first = ctx->laneFirst[k], cnt = ctx->laneFirst[k + 1] - first;
+            ChunkHdr *hdrs = ctx->d_hdrs.p + k;
+            ChunkHdr *hostHdrs = h_hdrs_dev + k;
+            LVN_TRACE_EV(0);
+            LaneArenas lane;
+            lane.caps = caps;
+            lane.base.edges = caps.edges * k; lane.base.nodes = caps.nodes * k;
+            lane.base.quads = caps.quads * k; lane.base.seams = caps.seams * k;
+            lane.ctr = lane_counters_dev(k);
+            lane.edgeTiles = ctx->d_edgeTiles.p + (size_t)tileCap * k;
+            lane.nodeTiles = ctx->d_nodeTiles.p + (size_t)tileCap * k;
+            lane.tileCap = tileCap;
+            ctx->laneBase[k] = lane.base;
+            {
+                StageTimer t(ctx, LVN_STAGE_CLASSIFY, 1);
+                launch_rows(d, ctx->d_descs.p, first, cnt, ctx->d_heights.p, ctx->d_colMin.p, ctx->d_colMax.p, hdrs, hostHdrs,
+                            ws, lane, ls);
             }
-            launch_leaves(dp, d, ctx->d_descs.p, n, ctx->d_hdrs.p, ws, ctx->d_edgeInfo.p, ctx->d_vertices.p,
-                          ctx->d_tris.p, ctx->d_seams.p, dbg, st);
+            LVN_TRACE_EV(1);
+            {
+                StageTimer t(ctx, LVN_STAGE_HERMITE, 1);
+                launch_hermite(dp, d, ctx->d_descs.p, hdrs, ws, lane, ctx->d_heights.p, ctx->d_edgeKeys.p,
+                               ctx->d_edgeInfo.p, ls);
+            }
+            LVN_TRACE_EV(2);
+            {
+                StageTimer t(ctx, LVN_STAGE_LEAVES, 1);
+                NodeDebug dbg = {};
+                if (opts.debug) {
+                    dbg.codes = ctx->d_dbgCodes.p; dbg.edgeMasks = ctx->d_dbgMasks.p; dbg.matWords = ctx->d_dbgMats.p;
+                    dbg.qefs = ctx->d_dbgQefs.p; dbg.positions = ctx->d_dbgPos.p; dbg.normals = ctx->d_dbgNrm.p;
+                }
+                launch_leaves(dp, d, ctx->d_descs.p, hdrs, ws, lane, (ArenaCounters *)(h_hdrs_dev + first + cnt + k),
+                              ctx->d_edgeInfo.p, ctx->d_vertices.p, ctx->d_tris.p, ctx->d_seams.p, dbg, ls);
+            }
+            LVN_TRACE_EV(3);
+            LVN_TRACE_EV(4);
+            if (S > 1) CU(cudaEventRecord(ctx->evLane[k], ls));
+            return LVN_SUCCESS;
+        };
+
+        bool overflow = false, hostFull = false;
+        if (!out) {
+            for (int k = 0; k < S; k++) LV(enqueue_lane(k));
+        } else {
+            // host path: keep two lanes queued ahead of the one being drained over the copy
+            // engine, so that neither the SMs nor the PCIe link wait for the host
+            int64_t hv = 0, ht = 0, hs = 0;
+            int issued = 0;
+            for (int k = 0; k < S; k++) {
+                while (issued < S && issued < k + 2) LV(enqueue_lane(issued++));
+                if (overflow || hostFull) continue;   // keep issuing: the retry needs every lane's counts
+                if (S > 1) CU(cudaEventSynchronize(ctx->evLane[k]));
+                else CU(cudaStreamSynchronize(st));
+                const ArenaCounters c = *lane_counters_host(k);
+                if (c.overflow) { overflow = true; continue; }
+                ctx->hostBase[k][0] = hv; ctx->hostBase[k][1] = ht; ctx->hostBase[k][2] = hs;
+                if (hv + c.nodes > out->vertexCapacity || ht + 2 * (int64_t)c.quads > out->triangleCapacity ||
+                    hs + c.seams > out->seamCapacity) { hostFull = true; continue; }
+                const ArenaCaps &b = ctx->laneBase[k];
+                cudaStream_t cs = S > 1 ? ctx->copyStream : st;
+                if (c.nodes) CU(cudaMemcpyAsync(out->vertices + hv, ctx->d_vertices.p + b.nodes, (size_t)c.nodes * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToHost, cs));
+                if (c.quads) CU(cudaMemcpyAsync(out->triangles + ht, ctx->d_tris.p + (size_t)b.quads * 6, (size_t)c.quads * 6 * sizeof(int), cudaMemcpyDeviceToHost, cs));
+                if (c.seams) CU(cudaMemcpyAsync(out->seams + hs, ctx->d_seams.p + b.seams, (size_t)c.seams * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToHost, cs));
+                hv += c.nodes; ht += 2 * (int64_t)c.quads; hs += c.seams;
+                if (ctx->trace) {
+                    while (ctx->traceCopyEv.size() < (size_t)S) { cudaEvent_t e; cudaEventCreate(&e); ctx->traceCopyEv.push_back(e); }
+                    cudaEventRecord(ctx->traceCopyEv[k], cs);
+                }
+            }
         }
-        CU(cudaMemcpyAsync(ctx->h_hdrs.p, ctx->d_hdrs.p, n * sizeof(ChunkHdr), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, sizeof(ArenaCounters), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+#undef LVN_TRACE_EV
+        LV(join_lanes(ctx, R, out != nullptr && S > 1));
         CU(cudaGetLastError());
         collect_stage_times(ctx);
-        const ArenaCounters &c = *ctx->h_counters.p;
-        if (!c.overflow) {
-            ctx->lastCounters = c;
+        if (ctx->trace) {
+            fprintf(stderr, "[lvn trace] n=%d lanes=%d streams=%d  (us since fork: start rows|hermite|leaves|d2h|end)\n", n, S, R);
+            for (int k = 0; k < S; k++) {
+                float t[5];
+                for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ctx->traceEv[0], ctx->traceEv[1 + 5 * k + i]);
+                float tc = 0.f;
+                if (out && !overflow && !hostFull && ctx->traceCopyEv.size() >= (size_t)S)
+                    cudaEventElapsedTime(&tc, ctx->traceEv[0], ctx->traceCopyEv[k]);
+                fprintf(stderr, "[lvn trace]  lane %2d stream %d: %7.1f %7.1f %7.1f %7.1f %7.1f  copied %7.1f\n", k, k % R,
+                        t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, tc * 1e3);
+            }
+        }
+
+        ArenaCounters tot = {}, mx = {};
+        for (int k = 0; k < S; k++) {
+            const ArenaCounters c = *lane_counters_host(k);
+            ctx->laneCounters[k] = c;
+            tot.edges += c.edges; tot.nodes += c.nodes; tot.quads += c.quads; tot.seams += c.seams;
+            tot.nonEmpty += c.nonEmpty; tot.overflow |= c.overflow;
+            mx.edges = std::max(mx.edges, c.edges); mx.nodes = std::max(mx.nodes, c.nodes);
+            mx.quads = std::max(mx.quads, c.quads); mx.seams = std::max(mx.seams, c.seams);
+        }
+        if (!tot.overflow) {
+            ctx->lastCounters = tot;
             int64_t ey = 0;
-            for (int i = 0; i < n; i++) ey += ctx->h_hdrs.p[i].Ey;
-            ctx->stats.edges += c.edges; ctx->stats.edgesY += ey; ctx->stats.nodes += c.nodes;
-            ctx->stats.triangles += 2 * (int64_t)c.quads; ctx->stats.seamNodes += c.seams;
-            ctx->stats.chunks += n; ctx->stats.nonEmptyChunks += c.nonEmpty;
-            if (g.densityKind == 0) ctx->stats.terrainEvals += 4 * ey + 19 * ((int64_t)c.edges - ey);
+            for (int k = 0; k < S; k++)
+                for (int p = ctx->laneFirst[k]; p < ctx->laneFirst[k + 1]; p++) ey += ctx->h_hdrs.p[p + k].Ey;
+            ctx->stats.edges += tot.edges; ctx->stats.edgesY += ey; ctx->stats.nodes += tot.nodes;
+            ctx->stats.triangles += 2 * (int64_t)tot.quads; ctx->stats.seamNodes += tot.seams;
+            ctx->stats.chunks += n; ctx->stats.nonEmptyChunks += tot.nonEmpty;
+            if (g.densityKind == 0) ctx->stats.terrainEvals += 4 * ey + 19 * ((int64_t)tot.edges - ey);
+            if (out) {
+                if (hostFull) return LVN_ERR_CAPACITY;
+                ctx->hostLayout = true;
+            }
             return LVN_SUCCESS;
         }
-        // grow to what this batch asked for (+12%) and run again
-        LV(ctx->d_edgeKeys.reserve((size_t)c.edges + c.edges / 8 + 1024));
+        // grow every lane's slice to what the fullest lane asked for (+12%) and run again: the
+        // counters keep counting past the capacity, so one retry suffices
+        LV(ctx->d_edgeKeys.reserve((size_t)S * ((size_t)mx.edges + mx.edges / 8 + 1024)));
         LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
-        LV(ctx->d_vertices.reserve((size_t)c.nodes + c.nodes / 8 + 1024));
-        LV(ctx->d_tris.reserve(((size_t)c.quads + c.quads / 8 + 1024) * 6));
-        LV(ctx->d_seams.reserve((size_t)c.seams + c.seams / 8 + 1024));
+        LV(ctx->d_vertices.reserve((size_t)S * ((size_t)mx.nodes + mx.nodes / 8 + 1024)));
+        LV(ctx->d_tris.reserve((size_t)S * ((size_t)mx.quads + mx.quads / 8 + 1024) * 6));
+        LV(ctx->d_seams.reserve((size_t)S * ((size_t)mx.seams + mx.seams / 8 + 1024)));
     }
     return LVN_ERR_CAPACITY;
 }
 
+// per-chunk results in the caller's chunk order; offsets address the device arenas, or the host
+// arenas after a host-path batch
 static void fill_results(lvn_meshgen *ctx, int n, lvn_chunk_result *results)
 {
-    for (int i = 0; i < n; i++) {
-        const ChunkHdr &h = ctx->h_hdrs.p[i];
-        lvn_chunk_result &r = results[i];
-        r.numEdges = h.E;
-        // a chunk whose octree yields no quad exports an empty mesh buffer, but still its seam
-        // nodes (GenerateMeshFromOctree returns before filling the buffer, compute_octree.cpp:227-232)
-        r.numVertices = h.Q > 0 ? h.N : 0;
-        r.numTriangles = 2 * h.Q;
-        r.numSeamNodes = h.S;
-        r.vertexOffset = h.nodeBase;
-        r.triangleOffset = 2 * h.quadBase;
-        r.seamOffset = h.seamBase;
-        r.status = h.status;
+    for (int k = 0; k < ctx->numLanes; k++) {
+        const ArenaCaps &b = ctx->laneBase[k];
+        for (int p = ctx->laneFirst[k]; p < ctx->laneFirst[k + 1]; p++) {
+            const ChunkHdr &h = ctx->h_hdrs.p[p + k];   // lane k's headers sit k counter slots further
+            lvn_chunk_result &r = results[ctx->perm[p]];
+            r.numEdges = h.E;
+            // a chunk whose octree yields no quad exports an empty mesh buffer, but still its seam
+            // nodes (GenerateMeshFromOctree returns before filling the buffer, compute_octree.cpp:227-232)
+            r.numVertices = h.Q > 0 ? h.N : 0;
+            r.numTriangles = 2 * h.Q;
+            r.numSeamNodes = h.S;
+            if (ctx->hostLayout) {
+                r.vertexOffset = (int32_t)(ctx->hostBase[k][0] + (h.N ? h.nodeBase - (int)b.nodes : 0));
+                r.triangleOffset = (int32_t)(ctx->hostBase[k][1] + 2 * (h.Q ? h.quadBase - (int)b.quads : 0));
+                r.seamOffset = (int32_t)(ctx->hostBase[k][2] + (h.S ? h.seamBase - (int)b.seams : 0));
+            } else {
+                r.vertexOffset = h.nodeBase;
+                r.triangleOffset = 2 * h.quadBase;
+                r.seamOffset = h.seamBase;
+            }
+            r.status = h.status;
+        }
     }
+    (void)n;
 }
 
 extern "C" int lvn_meshgen_generate_batch_device(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
@@ -769,17 +1027,13 @@ extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const i
 {
     if (!results) return LVN_ERR_INVALID_VALUE;
     BatchOpts opts;
-    LV(run_batch(ctx, nChunks, chunkMinSize, opts));
-    fill_results(ctx, nChunks, results);
-    const ArenaCounters &c = ctx->lastCounters;
-    if ((int64_t)c.nodes > vertexCapacity || 2 * (int64_t)c.quads > triangleCapacity || (int64_t)c.seams > seamCapacity)
-        return LVN_ERR_CAPACITY;
-    cudaStream_t st = ctx->stream;
-    if (c.nodes) CU(cudaMemcpyAsync(vertices, ctx->d_vertices.p, (size_t)c.nodes * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToHost, st));
-    if (c.quads) CU(cudaMemcpyAsync(triangles, ctx->d_tris.p, (size_t)c.quads * 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (c.seams) CU(cudaMemcpyAsync(seamNodes, ctx->d_seams.p, (size_t)c.seams * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return LVN_SUCCESS;
+    HostOut out = {vertices, vertexCapacity, triangles, triangleCapacity, seamNodes, seamCapacity};
+    const int rc = run_batch(ctx, nChunks, chunkMinSize, opts, &out);
+    if (rc == LVN_SUCCESS || rc == LVN_ERR_CAPACITY) {
+        // on LVN_ERR_CAPACITY the counts say what the caller must provide
+        if (ctx && ctx->numLanes) fill_results(ctx, nChunks, results);
+    }
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

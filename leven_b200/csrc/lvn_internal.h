@@ -45,10 +45,24 @@ struct ArenaCounters {
     unsigned int edges, nodes, quads, seams;
     unsigned int overflow;
     unsigned int nonEmpty;
-    unsigned int pad[2];
+    unsigned int edgeTiles, nodeTiles;   // entries of the tile directories
 };
 
+// Tile directories: the Hermite and leaf kernels run one block per tile of LVN_TILE consecutive
+// edges / nodes of one chunk, so their grids are flat over the surface of the whole lane and
+// empty chunks cost nothing.
+struct TileRef { int chunk, first; };
+constexpr int LVN_TILE = 128;
+
 struct ArenaCaps { unsigned int edges, nodes, quads, seams; };
+
+// one lane's slices of the arenas, tile directories and counters
+struct LaneArenas {
+    ArenaCaps caps, base;             // capacity of the slice and where it starts
+    ArenaCounters *ctr;
+    TileRef *edgeTiles, *nodeTiles;   // the lane's directories
+    unsigned int tileCap;             // entries per directory
+};
 
 // Geometry of a mesh-generation context (compute.cpp:245-252,271).
 struct Dims {
@@ -57,14 +71,22 @@ struct Dims {
     int depth;          // MAX_OCTREE_DEPTH
 };
 
-// Per-chunk scratch that links the classify kernel to the leaf kernel.
+// A chunk is cut into slabs of LVN_SLAB_Z z layers (one k_rows block each); row offsets are
+// relative to the slab, the slab records hold the slab's exclusive base.
+constexpr int LVN_SLAB_Z = 6;
+constexpr int LVN_MAX_SLABS = 11;   // ceil(66 / 6)
+
+// Per-chunk scratch that links k_rows to the Hermite and leaf kernels.
 struct ChunkScratch {
     unsigned long long *bitsLo;   // [n][F*F] solid bits x 0..63 of row (z*F + y)
     unsigned int *bitsHi;         // [n][F*F] solid bits x 64..
-    unsigned int *rowE;           // [n][H*H] exclusive edge offsets per Hermite row (z*H + y)
-    unsigned int *rowN;           // [n][V*V] exclusive node offsets per voxel row (z*V + y)
+    unsigned int *rowE;           // [n][H*H] slab-relative exclusive edge offsets per Hermite row (z*H + y)
+    unsigned int *rowN;           // [n][V*V] slab-relative exclusive node offsets per voxel row (z*V + y)
     unsigned int *rowQ;           // [n][V*V] quads
     unsigned int *rowS;           // [n][V*V] seam nodes
+    uint4 *slab;                  // [n][LVN_MAX_SLABS] exclusive (edge, node, quad, seam) base of each slab
+    unsigned int *slabEy;         // [n][LVN_MAX_SLABS] y edges of each slab (stage accounting)
+    unsigned int *ticket;         // [n] slabs finished; zero between batches
 };
 
 struct DensityParams {
@@ -86,20 +108,24 @@ struct NodeDebug {
 };
 
 // ---- launchers (kernels_chunk.cu) ----------------------------------------
+// colMin / colMax: per column set, the ordered-int keys of the smallest / largest height
+// (initialise with memset 0x7f / 0x80 before launch_columns)
 void launch_columns(const DensityParams &dp, const Dims &d, const int4 *colSetOrigins, int numColSets,
-                    float *heights, cudaStream_t s);
+                    float *heights, int *colMin, int *colMax, cudaStream_t s);
 void launch_field_from_heights(const Dims &d, const ChunkDesc *descs, int n, const float *heights,
                                int defaultMaterial, uint8_t *const *fields, cudaStream_t s);
 void launch_field_density(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, int n,
                           uint8_t *const *fields, cudaStream_t s);
-void launch_classify(const Dims &d, const ChunkDesc *descs, int n, const float *heights,
-                     ChunkHdr *hdrs, ChunkScratch ws, ArenaCounters *counters, ArenaCaps caps,
-                     int *edgeKeys, cudaStream_t s);
-void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, int n,
-                    const ChunkHdr *hdrs, const float *heights, const int *edgeKeys, float4 *edgeInfo,
+// the chunk kernels work on descs[first .. first + n): one lane of a batch (api.cu: run_batch)
+// hostHdrs / hostCounters: mapped pinned mirrors written directly by the kernels
+void launch_rows(const Dims &d, const ChunkDesc *descs, int first, int n, const float *heights,
+                 const int *colMin, const int *colMax, ChunkHdr *hdrs, ChunkHdr *hostHdrs, ChunkScratch ws,
+                 LaneArenas lane, cudaStream_t s);
+void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
+                    ChunkScratch ws, LaneArenas lane, const float *heights, int *edgeKeys, float4 *edgeInfo,
                     cudaStream_t s);
-void launch_leaves(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, int n,
-                   const ChunkHdr *hdrs, ChunkScratch ws, const float4 *edgeInfo,
+void launch_leaves(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
+                   ChunkScratch ws, LaneArenas lane, ArenaCounters *hostCounters, const float4 *edgeInfo,
                    lvn_mesh_vertex *vertices, int *triIndices, lvn_seam_node_info *seams,
                    NodeDebug dbg, cudaStream_t s);
 
