@@ -63,7 +63,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -71,17 +71,22 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.marks = []
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
             time.sleep(0.5)      # let nvidia-smi attach before the timed region starts
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """wall-clock bounds of the timed regions: only samples taken inside count"""
+        self.marks.append(time.time())
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -92,16 +97,19 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        import datetime
         sm, mx, reasons = [], [], set()
+        lo, hi = (min(self.marks), max(self.marks)) if len(self.marks) >= 2 else (0.0, float("inf"))
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                clk, cmax, pw = float(f[1]), float(f[2]), float(f[3])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            if pw < 250.0:          # idle sample taken before / after the kernels ran
+            if ts < lo - 0.02 or ts > hi + 0.02:    # taken before / after the timed regions
                 continue
             sm.append(clk); mx.append(cmax)
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -119,6 +127,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from oracle import oracle as O
+    O.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1
     world = O.World(seed=SEED, default_material=0, voxels_per_chunk=V)
     ms = ring_chunks(0)
     threads = 1
@@ -251,6 +260,7 @@ def main():
     ctx.getStats(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.mark()
     dev_ms, wall = timed_region(step_device, args.steps)
     run_stats = ctx.getStats(reset=True)
     pipe = ctx.getPipeline()
@@ -259,6 +269,7 @@ def main():
         step_e2e()
     e2e_ms, e2e_wall = timed_region(step_e2e, args.steps)
     pipe_e2e = ctx.getPipeline()
+    sampler.mark()
     clocks = sampler.stop()
     # ---- per-kernel durations: the same step with one lane on one stream, so that every kernel
     #      runs alone between its two CUDA events (in the timed regions above kernels of
@@ -367,6 +378,7 @@ def main():
 
     if world_size == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O      # the checker's CPU port, timed as the reported baseline
+        O.set_num_threads(os.cpu_count() or 1)
         world = O.World(image=lc.Compute_GetNoiseImage(), default_material=0, voxels_per_chunk=V)
         world.batch_counts(ms[:32])
         t0 = time.perf_counter()

@@ -1704,6 +1704,18 @@ void lvo_chunk_free(lvo_chunk *c)
 
 /* CPU-baseline helper: the per-chunk work of Compute_GenerateChunkMesh with
  * cold caches, OpenMP over independent chunks. */
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline leg asks for the host's cores */
+int lvo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int lvo_generate_batch_counts(const lvo_world *w, int n, const int *minSize, int32_t *counts)
 {
     int i, threads = 1;

@@ -176,6 +176,7 @@ void lvo_chunk_free(lvo_chunk *);
 
 /* batch helper for the CPU baseline: n independent chunks, OpenMP over
  * chunks, no caches; counts[4*i..] = E, N, T, S.  Returns threads used. */
+int lvo_set_num_threads(int n);   /* OpenMP threads of the batch helper; returns the count in effect */
 int lvo_generate_batch_counts(const lvo_world *, int n, const int *minSize /* 4n */, int32_t *counts);
 
 #ifdef __cplusplus

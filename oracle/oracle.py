@@ -101,8 +101,14 @@ def lib():
         L.lvo_generate_chunk_mesh.argtypes = [P, P, I, P]
         L.lvo_chunk_free.argtypes = [P]
         L.lvo_generate_batch_counts.argtypes = [P, I, P, P]; L.lvo_generate_batch_counts.restype = I
+        L.lvo_set_num_threads.argtypes = [I]; L.lvo_set_num_threads.restype = I
         _lib = L
     return _lib
+
+
+def set_num_threads(n):
+    """OpenMP threads of World.batch_counts (torchrun exports OMP_NUM_THREADS=1); returns the count in effect"""
+    return lib().lvo_set_num_threads(int(n))
 
 
 def _ptr(a):

@@ -341,6 +341,15 @@ def test_default_material_and_seed(lc, oracle_mod):
         ref = check_chunk_stages(ctx, world, [0, cy * 256, 0])
         assert np.all((ref["matWords"] >> 8) == 7)
         ctx.destroy(); world.close()
+        # a default material that sorts AFTER MATERIAL_AIR (201): FindDominantMaterial's sorted-run
+        # scan (octree.cl:96-138) then starts on AIR and its tie rule can return AIR -- the quirk is
+        # part of the restated behaviour
+        assert lc.Compute_Initialise(0x7d3af, 250, 2) == 0
+        ctx = lc.Compute_MeshGenContext.create(64)
+        world = oracle_mod.World(image=lc.Compute_GetNoiseImage(), default_material=250, voxels_per_chunk=64)
+        ref = check_chunk_stages(ctx, world, [0, cy * 256, 0])
+        assert set(np.unique(ref["matWords"] >> 8)) <= {250, 201}
+        ctx.destroy(); world.close()
     finally:
         assert lc.Compute_Initialise(SEED, 0, 2) == 0
 
