@@ -7,8 +7,9 @@
 //   leven/src/compute_csg.cpp           ApplyCSGOperations
 //   leven/src/compute_cuckoo.cpp        table sizing, rehash loop
 //
-// One batch = four kernels and one host synchronisation (the reference: ~65 launches and ~10
-// blocking reads per chunk).
+// One batch = one column kernel plus three kernels per lane (k_rows -> k_hermite -> k_leaves) and
+// one host wait per lane (the reference: ~65 launches and ~10 blocking reads per chunk,
+// SURVEY.md 3.2).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>

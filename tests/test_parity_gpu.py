@@ -167,6 +167,69 @@ def test_batch_equals_single_chunks(lc, ctx, gpu_world, surface_cy):
         assert_float_parity(s["position"], ref["seams"]["position"], "batch seam position")
 
 
+def _chunk_bytes(res, V, T, S):
+    """per chunk: the raw bytes of its mesh and seam slices (layout-independent comparison)"""
+    out = []
+    for r in res:
+        v = V[r["vertexOffset"]: r["vertexOffset"] + r["numVertices"]]
+        t = T[r["triangleOffset"]: r["triangleOffset"] + r["numTriangles"]]
+        s = S[r["seamOffset"]: r["seamOffset"] + r["numSeamNodes"]]
+        out.append((v.tobytes(), t.tobytes(), s.tobytes()))
+    return out
+
+
+def test_pipeline_lanes_and_streams(lc, surface_cy):
+    """lanes x streams of the batch pipeline (lvn_meshgen_set_pipeline) change where a chunk's
+    slices land, never what is in them: every setting returns, per chunk, the bytes of the
+    one-lane run; host offsets tile the packed host arenas; a ragged last lane, a batch smaller
+    than the lane count and a first call that must grow its arenas are covered"""
+    c = lc.Compute_MeshGenContext.create(64)
+    try:
+        ms = ring(surface_cy, 3, 2)[:131]                  # 131 chunks: ragged lanes
+        assert c.setPipeline(1, 1) == 0
+        V = np.zeros(600000, lc.MeshVertex); T = np.zeros(1200000, lc.MeshTriangle); S = np.zeros(150000, lc.SeamNodeInfo)
+        rc, res0 = c.generateBatch(ms, V, T, S)            # cold context: arenas grow inside this call
+        assert rc == 0, lc.GetCLErrorString(rc)
+        want = _chunk_bytes(res0, V, T, S)
+        assert sum(len(w[0]) for w in want) > 0
+        for lanes, streams in ((2, 1), (2, 2), (4, 1), (5, 3), (8, 4), (32, 4), (0, 2)):
+            assert c.setPipeline(lanes, streams) == 0
+            V2 = np.zeros_like(V); T2 = np.zeros_like(T); S2 = np.zeros_like(S)
+            rc, res = c.generateBatch(ms, V2, T2, S2)
+            assert rc == 0, (lanes, streams, lc.GetCLErrorString(rc))
+            got_lanes, got_streams = c.getPipeline()
+            if lanes:
+                assert got_lanes == min(lanes, len(ms)) and got_streams == min(streams, got_lanes)
+            for k in ("numEdges", "numVertices", "numTriangles", "numSeamNodes", "status"):
+                assert np.array_equal(res[k], res0[k]), (lanes, streams, k)
+            assert _chunk_bytes(res, V2, T2, S2) == want, (lanes, streams)
+            # the host arenas are packed: slices of non-empty chunks tile [0, total)
+            ne = res[res["numSeamNodes"] > 0]
+            iv = sorted((int(r["seamOffset"]), int(r["seamOffset"] + r["numSeamNodes"])) for r in ne)
+            assert iv[0][0] == 0 and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+            assert iv[-1][1] == int(res["numSeamNodes"].sum())
+            # the device-resident pass agrees on the counts
+            rc, resd, view = c.generateBatchDevice(ms)
+            assert rc == 0
+            assert np.array_equal(resd["numTriangles"], res0["numTriangles"])
+            assert int(view.totalTriangles) == int(res0["numTriangles"].sum())
+        # fewer chunks than lanes
+        assert c.setPipeline(8, 2) == 0
+        few = ms[res0["numTriangles"] > 0][:3]
+        rc, resf = c.generateBatch(few, V, T, S)
+        assert rc == 0 and c.getPipeline()[0] == 3
+        idx = np.nonzero(res0["numTriangles"] > 0)[0][:3]
+        assert _chunk_bytes(resf, V, T, S) == [want[i] for i in idx]
+        # too-small host arenas: an error code and the counts the caller must provide
+        assert c.setPipeline(4, 1) == 0
+        rc, rese = c.generateBatch(ms, V[:100], T, S)
+        assert rc == lc.LVN_ERR_CAPACITY
+        assert np.array_equal(rese["numVertices"], res0["numVertices"])
+        assert c.setPipeline(33, 1) < 0 and c.setPipeline(2, 0) < 0 and c.setPipeline(2, 5) < 0
+    finally:
+        c.destroy()
+
+
 def test_batch_full_size_properties(lc, ctx, surface_cy):
     """config 2 at full size (512 chunks): size-independent properties -- offsets tile the arenas,
     every index addresses its own chunk's vertices, quads are consistent, a second run is identical"""
