@@ -328,18 +328,26 @@ def main():
          "achieved_tflops": col_sets * F2 * FLOP_PER_DENSITY / (stage_ms["columns"] * 1e-3) / 1e12
          if stage_ms["columns"] > 0 else 0.0,
          "peak_tflops": fp32_peak},
-        {"stage": "classify (S2+S4)", "bound": "hbm", "ms": stage_ms["classify"], "algorithmic_bytes": classify_bytes,
+        {"stage": "rows (S2+S4)", "bound": "hbm", "ms": stage_ms["classify"], "algorithmic_bytes": classify_bytes,
          "achieved_gbs": gbs(classify_bytes, stage_ms["classify"]), "peak_gbs": hbm_peak},
         {"stage": "hermite (S3)", "bound": "fp32", "ms": stage_ms["hermite"], "algorithmic_flop": herm_flop,
          "achieved_tflops": herm_tflops, "peak_tflops": fp32_peak},
         {"stage": "leaves (S5+S6+S8+S9+S10)", "bound": "hbm", "ms": stage_ms["leaves"], "algorithmic_bytes": leaves_bytes,
          "achieved_gbs": gbs(leaves_bytes, stage_ms["leaves"]), "peak_gbs": hbm_peak},
     ]
-    for s in stages:
+    # issue-slot view: executed warp instructions of the launch (ncu, profiles/latest_traffic.json)
+    # over the time it took here, against 4 schedulers x 148 SMs x the SM clock seen under load
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    issue_peak = 4 * 148 * sm_hz
+    for s, key in zip(stages, ("columns", "rows", "hermite", "leaves")):
         if s["bound"] == "fp32":
             s["frac"] = s["achieved_tflops"] / fp32_peak if fp32_peak else None
         else:
             s["frac"] = s["achieved_gbs"] / hbm_peak
+        inst = prof.get(key + "_warp_inst_per_launch")
+        if inst and s["ms"] > 0:
+            s["warp_inst_per_launch_ncu"] = inst
+            s["issue_frac"] = inst / (s["ms"] * 1e-3) / issue_peak
 
     h2d = nchunks * 16                                   # the caller's chunk list (4 ints per chunk)
     d2h = totV * 48 + totT * 12 + totS * 48 + nchunks * 32   # mesh + seam arenas + per-chunk results

@@ -23,6 +23,7 @@
 #ifndef LEVEN_COMPUTE_H
 #define LEVEN_COMPUTE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -206,6 +207,10 @@ int lvn_meshgen_set_stream(lvn_meshgen *ctx, void *cudaStream);
  * stream; the host-path batch call drains finished lanes over the copy engine meanwhile. */
 int lvn_meshgen_set_pipeline(lvn_meshgen *ctx, int lanes, int streams);
 int lvn_meshgen_get_pipeline(const lvn_meshgen *ctx, int *lanesOfLastBatch, int *streamsOfLastBatch);
+/* pinned host memory for the arenas of lvn_meshgen_generate_batch (NULL on failure): the lane
+ * copies then run at PCIe rate instead of through the driver's staging buffer */
+void *lvn_alloc_pinned(size_t bytes);
+void lvn_free_pinned(void *p);
 /* FP32 roofline denominator: independent FMA chains on every SM, CUDA-event timed (2 flop/FMA) */
 int lvn_measure_fp32_peak(double *tflops);
 int lvn_meshgen_get_stats(lvn_meshgen *ctx, lvn_stage_stats *out, int reset);

@@ -116,6 +116,8 @@ ABI = {
     "lvn_meshgen_set_stream": (_I, [_P, _P]),
     "lvn_meshgen_set_pipeline": (_I, [_P, _I, _I]),
     "lvn_meshgen_get_pipeline": (_I, [_P, _P, _P]),
+    "lvn_alloc_pinned": (_P, [C.c_size_t]),
+    "lvn_free_pinned": (None, [_P]),
     "lvn_measure_fp32_peak": (_I, [_P]),
     "lvn_find_next_prime": (_I, [_I]),
     "lvn_exclusive_scan": (_I, [_P, _P, _I]),
@@ -372,6 +374,33 @@ class Compute_MeshGenContext:
         out["ms"] = {n: s.ms[i] for i, n in enumerate(LVN_STAGES)}
         out["launches"] = {n: s.launches[i] for i, n in enumerate(LVN_STAGES)}
         return out
+
+
+class PinnedArray:
+    """numpy array in pinned host memory (lvn_alloc_pinned) for the arenas of generateBatch.
+    Keep the object alive while the array is in use."""
+
+    def __init__(self, n, dtype):
+        dtype = np.dtype(dtype)
+        self._L = lib()
+        self.nbytes = max(int(n), 1) * dtype.itemsize
+        self.ptr = self._L.lvn_alloc_pinned(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("lvn_alloc_pinned failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=max(int(n), 1))[:int(n)]
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._L.lvn_free_pinned(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def MeasureFP32Peak():

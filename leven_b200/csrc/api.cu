@@ -268,6 +268,13 @@ extern "C" int lvn_compute_initialise(int noiseSeed, unsigned int defaultMateria
     if (defaultMaterial > 255u) return LVN_ERR_INVALID_VALUE;   // materials are stored as u8
     if (g.deviceChosen) CU(cudaSetDevice(g.device));
     else CU(cudaGetDevice(&g.device));
+    {   // keep freed octree-cache blocks in the device's pool instead of returning them to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g.device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     g.initialised = true;
     g.defaultMaterial = (int)defaultMaterial;
     g.cuckooRng = std::mt19937();
@@ -347,18 +354,30 @@ struct FieldEntry {
     }
 };
 
-// GPUOctree (compute_local.h:44-50) reduced to what a later generateChunkMesh returns
+// GPUOctree (compute_local.h:44-50) reduced to what a later generateChunkMesh returns.  One
+// stream-ordered allocation from the device's memory pool per entry: cudaMalloc / cudaFree
+// would synchronise the device on every chunk request and eviction.
 struct OctreeEntry {
     int numNodes = 0, numQuads = 0, numSeams = 0;
+    void *block = nullptr;
     lvn_mesh_vertex *d_v = nullptr;
     int *d_t = nullptr;
     lvn_seam_node_info *d_s = nullptr;
-    void release()
+    int alloc(cudaStream_t st)
     {
-        if (d_v) cudaFree(d_v);
-        if (d_t) cudaFree(d_t);
-        if (d_s) cudaFree(d_s);
-        d_v = nullptr; d_t = nullptr; d_s = nullptr;
+        const size_t bv = (size_t)numNodes * sizeof(lvn_mesh_vertex), bs = (size_t)numSeams * sizeof(lvn_seam_node_info),
+                     bt = (size_t)numQuads * 6 * sizeof(int);
+        if (bv + bs + bt == 0) return LVN_SUCCESS;
+        CU(cudaMallocAsync(&block, bv + bs + bt, st));
+        d_v = (lvn_mesh_vertex *)block;                               // 48 B records first: 16 B alignment holds
+        d_s = (lvn_seam_node_info *)((char *)block + bv);
+        d_t = (int *)((char *)block + bv + bs);
+        return LVN_SUCCESS;
+    }
+    void release(cudaStream_t st)
+    {
+        if (block) cudaFreeAsync(block, st);
+        block = nullptr; d_v = nullptr; d_t = nullptr; d_s = nullptr;
     }
 };
 
@@ -471,7 +490,8 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->fields) kv.second.release();
-    for (auto &kv : ctx->octrees) kv.second.release();
+    for (auto &kv : ctx->octrees) kv.second.release(ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_colOrigins.release(); ctx->d_heights.release();
     ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
     ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release();
@@ -527,6 +547,15 @@ extern "C" int lvn_meshgen_get_pipeline(const lvn_meshgen *ctx, int *lanesOfLast
     if (streams) *streams = ctx->numStreams;
     return LVN_SUCCESS;
 }
+
+extern "C" void *lvn_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void lvn_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int lvn_measure_fp32_peak(double *tflops)
 {
@@ -1234,7 +1263,7 @@ extern "C" int lvn_meshgen_free_chunk_octree(lvn_meshgen *ctx, const int32_t min
     if (!ctx) return LVN_ERR_INVALID_VALUE;
     auto it = ctx->octrees.find(make_key(min, size));
     if (it != ctx->octrees.end()) {
-        it->second.release();
+        it->second.release(ctx->stream);
         ctx->octrees.erase(it);
     }
     return LVN_SUCCESS;
@@ -1281,18 +1310,10 @@ extern "C" int lvn_meshgen_generate_chunk_mesh(lvn_meshgen *ctx, const int32_t m
         if (h.E == 0) return LVN_SUCCESS;   // "no point in trying to construct the octree"
         OctreeEntry oe;
         oe.numNodes = h.N; oe.numQuads = h.Q; oe.numSeams = h.S;
-        if (h.N) {
-            CU(cudaMalloc((void **)&oe.d_v, (size_t)h.N * sizeof(lvn_mesh_vertex)));
-            CU(cudaMemcpyAsync(oe.d_v, ctx->d_vertices.p + h.nodeBase, (size_t)h.N * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToDevice, st));
-        }
-        if (h.Q) {
-            CU(cudaMalloc((void **)&oe.d_t, (size_t)h.Q * 6 * sizeof(int)));
-            CU(cudaMemcpyAsync(oe.d_t, ctx->d_tris.p + (size_t)h.quadBase * 6, (size_t)h.Q * 6 * sizeof(int), cudaMemcpyDeviceToDevice, st));
-        }
-        if (h.S) {
-            CU(cudaMalloc((void **)&oe.d_s, (size_t)h.S * sizeof(lvn_seam_node_info)));
-            CU(cudaMemcpyAsync(oe.d_s, ctx->d_seams.p + h.seamBase, (size_t)h.S * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToDevice, st));
-        }
+        LV(oe.alloc(st));
+        if (h.N) CU(cudaMemcpyAsync(oe.d_v, ctx->d_vertices.p + h.nodeBase, (size_t)h.N * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToDevice, st));
+        if (h.Q) CU(cudaMemcpyAsync(oe.d_t, ctx->d_tris.p + (size_t)h.quadBase * 6, (size_t)h.Q * 6 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        if (h.S) CU(cudaMemcpyAsync(oe.d_s, ctx->d_seams.p + h.seamBase, (size_t)h.S * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToDevice, st));
         oit = ctx->octrees.emplace(key, oe).first;
     }
     const OctreeEntry &oe = oit->second;

@@ -81,9 +81,11 @@ def main():
         d["hot_source_lines"] = hot_lines(rep)
         summary.append(d)
         t = d.get("dram__bytes_read.sum [B]", 0.0) + d.get("dram__bytes_write.sum [B]", 0.0)
-        for key in ("hermite", "leaves", "classify", "columns"):
+        for key in ("hermite", "leaves", "rows", "columns"):
             if "k_" + key in d["kernel"]:
                 traffic[key + "_dram_bytes_per_launch"] = t
+                # executed warp instructions of that launch: bench.py's issue-slot fraction
+                traffic[key + "_warp_inst_per_launch"] = d.get("smsp__inst_executed.sum [inst]", 0.0)
     json.dump(summary, open(os.path.join(here, f"{tag}_summary.json"), "w"), indent=1)
     with open(os.path.join(here, f"{tag}_summary.txt"), "w") as f:
         for d in summary:

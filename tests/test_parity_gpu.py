@@ -192,6 +192,11 @@ def test_pipeline_lanes_and_streams(lc, surface_cy):
         assert rc == 0, lc.GetCLErrorString(rc)
         want = _chunk_bytes(res0, V, T, S)
         assert sum(len(w[0]) for w in want) > 0
+        rc, _, view0 = c.generateBatchDevice(ms)
+        assert rc == 0
+        PV = lc.PinnedArray(int(view0.totalVertices), lc.MeshVertex)      # every node, also of chunks without quads
+        PT = lc.PinnedArray(int(view0.totalTriangles), lc.MeshTriangle)
+        PS = lc.PinnedArray(int(view0.totalSeamNodes), lc.SeamNodeInfo)
         for lanes, streams in ((2, 1), (2, 2), (4, 1), (5, 3), (8, 4), (32, 4), (0, 2)):
             assert c.setPipeline(lanes, streams) == 0
             V2 = np.zeros_like(V); T2 = np.zeros_like(T); S2 = np.zeros_like(S)
@@ -208,6 +213,10 @@ def test_pipeline_lanes_and_streams(lc, surface_cy):
             iv = sorted((int(r["seamOffset"]), int(r["seamOffset"] + r["numSeamNodes"])) for r in ne)
             assert iv[0][0] == 0 and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
             assert iv[-1][1] == int(res["numSeamNodes"].sum())
+            # pinned arenas sized exactly: same bytes per chunk
+            rc, resp = c.generateBatch(ms, PV.array, PT.array, PS.array)
+            assert rc == 0, (lanes, streams, lc.GetCLErrorString(rc))
+            assert _chunk_bytes(resp, PV.array, PT.array, PS.array) == want, (lanes, streams, "pinned")
             # the device-resident pass agrees on the counts
             rc, resd, view = c.generateBatchDevice(ms)
             assert rc == 0
@@ -226,6 +235,7 @@ def test_pipeline_lanes_and_streams(lc, surface_cy):
         assert rc == lc.LVN_ERR_CAPACITY
         assert np.array_equal(rese["numVertices"], res0["numVertices"])
         assert c.setPipeline(33, 1) < 0 and c.setPipeline(2, 0) < 0 and c.setPipeline(2, 5) < 0
+        PV.close(); PT.close(); PS.close()
     finally:
         c.destroy()
 
