@@ -344,12 +344,12 @@ struct FieldEntry {
     unsigned int prime = 0;
     unsigned int params[8] = {0};
     int cuckooRetries = 0;
-    void release()
+    void release(cudaStream_t st)   // stream-ordered pool, like the octree entries
     {
-        if (d_field) cudaFree(d_field);
-        if (d_keys) cudaFree(d_keys);
-        if (d_info) cudaFree(d_info);
-        if (d_table) cudaFree(d_table);
+        if (d_field) cudaFreeAsync(d_field, st);
+        if (d_keys) cudaFreeAsync(d_keys, st);
+        if (d_info) cudaFreeAsync(d_info, st);
+        if (d_table) cudaFreeAsync(d_table, st);
         d_field = nullptr; d_keys = nullptr; d_info = nullptr; d_table = nullptr;
     }
 };
@@ -417,6 +417,7 @@ struct lvn_meshgen {
     // csg scratch
     DevBuf<unsigned int> d_touched, d_csgCounts;
     DevBuf<CsgOpDev> d_ops;
+    DevBuf<CsgChunk> d_csgChunks;
 
     PinBuf<ChunkDesc> h_descs;
     PinBuf<ChunkHdr> h_hdrs;
@@ -489,7 +490,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
 {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    for (auto &kv : ctx->fields) kv.second.release();
+    for (auto &kv : ctx->fields) kv.second.release(ctx->stream);
     for (auto &kv : ctx->octrees) kv.second.release(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_colOrigins.release(); ctx->d_heights.release();
@@ -501,7 +502,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_colMin.release(); ctx->d_colMax.release(); ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
-    ctx->d_ops.release();
+    ctx->d_ops.release(); ctx->d_csgChunks.release();
     ctx->h_descs.release(); ctx->h_hdrs.release(); ctx->h_colOrigins.release();
     ctx->h_small.release();
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -639,6 +640,7 @@ static void colour_for_size(int size, float rgb[3])
 struct BatchOpts {
     bool debug = false;          // fill the per-node stage dumps
     bool ignoreFieldCache = false;
+    bool singleLane = false;     // keep descriptors / headers in the caller's order
 };
 
 struct HostOut {   // caller-owned destination of lvn_meshgen_generate_batch
@@ -680,7 +682,7 @@ static void choose_pipeline(const lvn_meshgen *ctx, int n, const BatchOpts &opts
         streams = hostPath ? 1 : 2;
     }
     // per-stage event timing and the stage dumps want one kernel at a time on one stream
-    if (ctx->profiling || opts.debug) lanes = 1;
+    if (ctx->profiling || opts.debug || opts.singleLane) lanes = 1;
     lanes = std::max(1, std::min(std::min(lanes, LVN_MAX_LANES), n));
     streams = lanes == 1 ? 1 : std::max(1, std::min(std::min(streams, LVN_MAX_STREAMS), lanes));
 }
@@ -1067,7 +1069,7 @@ extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const i
 }
 
 // ---------------------------------------------------------------------------
-// cuckoo table of a field entry (compute_cuckoo.cpp:49-138)
+// cuckoo tables of field entries (compute_cuckoo.cpp:49-138), many at a time
 // ---------------------------------------------------------------------------
 static void draw_cuckoo_params(unsigned int *params8)
 {
@@ -1075,133 +1077,199 @@ static void draw_cuckoo_params(unsigned int *params8)
     for (int i = 0; i < 8; i++) params8[i] = distribution(g.cuckooRng);
 }
 
-static int build_cuckoo(lvn_meshgen *ctx, const unsigned int *d_keys, unsigned int count,
-                        unsigned long long **d_table, unsigned int *prime, unsigned int *params8, int *retries)
+// Cuckoo_InitialiseTable + Cuckoo_InsertKeys for every entry of the list: all fills and inserts
+// are queued, one host wait reads every failure flag, entries whose insertion failed are
+// rehashed with fresh parameters (the reference's loop, compute_cuckoo.cpp:89-132).
+static int build_cuckoo_tables(lvn_meshgen *ctx, const std::vector<FieldEntry *> &entries)
 {
     cudaStream_t st = ctx->stream;
-    StageTimer t(ctx, LVN_STAGE_CUCKOO, 0);
-    const unsigned int want = std::max(2048u, count * 2u);   // MIN_TABLE_SIZE
-    *prime = (unsigned int)host_find_next_prime((int)want);
-    if (*d_table) { cudaFree(*d_table); *d_table = nullptr; }
-    CU(cudaMalloc((void **)d_table, (size_t)*prime * sizeof(unsigned long long)));
-    LV(ctx->d_csgCounts.reserve(8));
-    LV(ctx->h_small.reserve(8));
-    for (int attempt = 0; attempt < 64; attempt++) {
-        draw_cuckoo_params(params8);
-        launch_fill_u64(*d_table, *prime, ~0ull, st);
-        CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, sizeof(unsigned int), st));
-        launch_cuckoo_insert(d_keys, count, *d_table, *prime, params8, ctx->d_csgCounts.p, st);
-        ctx->stats.launches[LVN_STAGE_CUCKOO] += 2;
-        CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (ctx->h_small.p[0] == 0) { if (retries) *retries = attempt; return LVN_SUCCESS; }
+    std::vector<FieldEntry *> todo;
+    for (FieldEntry *fe : entries) {
+        if (fe->d_table) { cudaFreeAsync(fe->d_table, st); fe->d_table = nullptr; }
+        fe->prime = 0;
+        fe->cuckooRetries = 0;
+        if (fe->numEdges <= 0) continue;
+        fe->prime = (unsigned int)host_find_next_prime((int)std::max(2048u, (unsigned int)fe->numEdges * 2u));   // MIN_TABLE_SIZE
+        CU(cudaMallocAsync((void **)&fe->d_table, (size_t)fe->prime * sizeof(unsigned long long), st));
+        todo.push_back(fe);
     }
-    return LVN_CL_ERROR;
+    if (todo.empty()) return LVN_SUCCESS;
+    StageTimer t(ctx, LVN_STAGE_CUCKOO, 0);
+    LV(ctx->d_csgCounts.reserve(todo.size()));
+    LV(ctx->h_small.reserve(todo.size()));
+    for (int attempt = 0; attempt < 64 && !todo.empty(); attempt++) {
+        CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, todo.size() * sizeof(unsigned int), st));
+        for (size_t i = 0; i < todo.size(); i++) {
+            FieldEntry *fe = todo[i];
+            draw_cuckoo_params(fe->params);
+            launch_fill_u64(fe->d_table, fe->prime, ~0ull, st);
+            launch_cuckoo_insert((const unsigned int *)fe->d_keys, (unsigned int)fe->numEdges, fe->d_table, fe->prime, fe->params,
+                                 ctx->d_csgCounts.p + i, st);
+            fe->cuckooRetries = attempt;
+            ctx->stats.launches[LVN_STAGE_CUCKOO] += 2;
+        }
+        CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, todo.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<FieldEntry *> failed;
+        for (size_t i = 0; i < todo.size(); i++)
+            if (ctx->h_small.p[i] != 0) failed.push_back(todo[i]);
+        todo.swap(failed);
+    }
+    return todo.empty() ? LVN_SUCCESS : LVN_CL_ERROR;
 }
 
 // ---------------------------------------------------------------------------
 // density-field cache (LoadDensityField / StoreDensityField, compute_density_field.cpp:235-308)
 // ---------------------------------------------------------------------------
 
-// GenerateDefaultDensityField + FindDefaultEdges into a persistent entry
-static int materialise_default_field(lvn_meshgen *ctx, const int32_t min[3], int size, FieldEntry &fe)
+// GenerateDefaultDensityField + FindDefaultEdges into persistent entries, n chunks in one pass of
+// the path.  The entries come without cuckoo tables (an edit that follows rebuilds them anyway).
+static int materialise_default_fields(lvn_meshgen *ctx, int n, const int32_t *minSize, std::vector<FieldEntry> &out)
 {
+    out.assign(n, FieldEntry());
+    if (n <= 0) return LVN_SUCCESS;
     const Dims &d = ctx->dims;
     const size_t F3 = (size_t)d.F * d.F * d.F;
-    int32_t ms[4] = {min[0], min[1], min[2], size};
     BatchOpts opts;
     opts.ignoreFieldCache = true;
-    LV(run_batch(ctx, 1, ms, opts));
+    opts.singleLane = true;     // descriptors and headers stay in the caller's order
+    LV(run_batch(ctx, n, minSize, opts));
     cudaStream_t st = ctx->stream;
-    const ChunkHdr &h = ctx->h_hdrs.p[0];
-    CU(cudaMalloc((void **)&fe.d_field, F3));
+    std::vector<uint8_t *> ptrs(n);
+    for (int i = 0; i < n; i++) {
+        const ChunkHdr &h = ctx->h_hdrs.p[i];
+        FieldEntry &fe = out[i];
+        CU(cudaMallocAsync((void **)&fe.d_field, F3, st));
+        ptrs[i] = fe.d_field;
+        fe.numEdges = h.E;
+        fe.lastCSGOperation = 0;
+        if (h.E > 0) {
+            CU(cudaMallocAsync((void **)&fe.d_keys, (size_t)h.E * sizeof(int), st));
+            CU(cudaMallocAsync((void **)&fe.d_info, (size_t)h.E * sizeof(float4), st));
+            CU(cudaMemcpyAsync(fe.d_keys, ctx->d_edgeKeys.p + h.edgeBase, (size_t)h.E * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(fe.d_info, ctx->d_edgeInfo.p + h.edgeBase, (size_t)h.E * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        }
+        if (g.densityKind != 0)
+            CU(cudaMemcpyAsync(fe.d_field, ctx->d_tmpFields.p + (size_t)i * F3, F3, cudaMemcpyDeviceToDevice, st));
+    }
     if (g.densityKind == 0) {
         StageTimer t(ctx, LVN_STAGE_FIELD, 1);
-        LV(ctx->d_fieldPtrs.reserve(1));
-        CU(cudaMemcpyAsync(ctx->d_fieldPtrs.p, &fe.d_field, sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
-        launch_field_from_heights(d, ctx->d_descs.p, 1, ctx->d_heights.p, g.defaultMaterial, ctx->d_fieldPtrs.p, st);
-    } else {
-        CU(cudaMemcpyAsync(fe.d_field, ctx->d_tmpFields.p, F3, cudaMemcpyDeviceToDevice, st));
+        LV(ctx->d_fieldPtrs.reserve(n));
+        CU(cudaMemcpyAsync(ctx->d_fieldPtrs.p, ptrs.data(), n * sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
+        launch_field_from_heights(d, ctx->d_descs.p, n, ctx->d_heights.p, g.defaultMaterial, ctx->d_fieldPtrs.p, st);
+        CU(cudaStreamSynchronize(st));   // ptrs must outlive the upload
     }
-    fe.numEdges = h.E;
-    fe.lastCSGOperation = 0;
-    if (h.E > 0) {
-        CU(cudaMalloc((void **)&fe.d_keys, (size_t)h.E * sizeof(int)));
-        CU(cudaMalloc((void **)&fe.d_info, (size_t)h.E * sizeof(float4)));
-        CU(cudaMemcpyAsync(fe.d_keys, ctx->d_edgeKeys.p + h.edgeBase, (size_t)h.E * sizeof(int), cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(fe.d_info, ctx->d_edgeInfo.p + h.edgeBase, (size_t)h.E * sizeof(float4), cudaMemcpyDeviceToDevice, st));
-    }
-    CU(cudaStreamSynchronize(st));
-    if (h.E > 0)
-        LV(build_cuckoo(ctx, (const unsigned int *)fe.d_keys, (unsigned int)h.E, &fe.d_table, &fe.prime, fe.params, &fe.cuckooRetries));
     return LVN_SUCCESS;
 }
 
-// ApplyCSGOperations, compute_csg.cpp:11-220
-static int apply_csg_to_field(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
-                              const int32_t min[3], int size, FieldEntry &fe)
+// One chunk of a batched edit: the field it applies to and its own op list (replayed stored ops
+// differ from chunk to chunk).
+struct CsgItem {
+    FieldEntry *fe;
+    int32_t ms[4];
+    const lvn_csg_operation_info *ops;
+    int numOps;
+};
+
+// ApplyCSGOperations, compute_csg.cpp:11-220, for many chunks: three batched launches, two host
+// waits (the counts that size the new edge lists; the hash-table insert flags).
+static int apply_csg_items(lvn_meshgen *ctx, const std::vector<CsgItem> &items)
 {
-    if (numOps <= 0) return LVN_SUCCESS;
+    const int n = (int)items.size();
+    if (n == 0) return LVN_SUCCESS;
     const Dims &d = ctx->dims;
     cudaStream_t st = ctx->stream;
-    int32_t ms[4] = {min[0], min[1], min[2], size};
-    ChunkDesc cd;
-    LV(fill_desc(ctx, ms, cd));
-
-    std::vector<CsgOpDev> hops(numOps);
-    for (int i = 0; i < numOps; i++) {
-        const lvn_csg_operation_info &o = ops[i];
-        if (o.material < 0 || o.material > 255 || (o.brushShape != 0 && o.brushShape != 1) || (o.type != 0 && o.type != 1))
-            return LVN_ERR_INVALID_VALUE;
-        CsgOpDev &v = hops[i];
-        v.type = o.type; v.shape = o.brushShape; v.material = o.material; v.pad = 0;
-        v.ox = o.origin[0]; v.oy = o.origin[1]; v.oz = o.origin[2];
-        v.dx = o.dimensions[0]; v.dy = o.dimensions[1]; v.dz = o.dimensions[2];
-        v.c = cosf(o.rotateY);   // pR(), hg_sdf.glsl:460-463; host libm so that every
-        v.s = sinf(o.rotateY);   // implementation fed the same op sees the same rotation
-    }
+    std::vector<CsgOpDev> hops;
+    std::vector<CsgChunk> hc(n);
     const size_t numWords = ((size_t)3 * d.H * d.H * d.H + 31) / 32;
-    LV(ctx->d_ops.reserve(numOps));
-    LV(ctx->d_touched.reserve(numWords));
-    LV(ctx->d_csgCounts.reserve(8));
-    LV(ctx->h_small.reserve(8));
-    CU(cudaMemcpyAsync(ctx->d_ops.p, hops.data(), numOps * sizeof(CsgOpDev), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(ctx->d_touched.p, 0, numWords * sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, 8 * sizeof(unsigned int), st));
+    for (int i = 0; i < n; i++) {
+        const CsgItem &it = items[i];
+        ChunkDesc cd;
+        LV(fill_desc(ctx, it.ms, cd));
+        CsgChunk &c = hc[i];
+        memset(&c, 0, sizeof(c));
+        c.ox = cd.ox; c.oy = cd.oy; c.oz = cd.oz; c.scale = cd.scale;
+        c.opFirst = (int)hops.size();
+        c.numOps = it.numOps;
+        for (int k = 0; k < it.numOps; k++) {
+            const lvn_csg_operation_info &o = it.ops[k];
+            if (o.material < 0 || o.material > 255 || (o.brushShape != 0 && o.brushShape != 1) || (o.type != 0 && o.type != 1))
+                return LVN_ERR_INVALID_VALUE;
+            CsgOpDev v;
+            v.type = o.type; v.shape = o.brushShape; v.material = o.material; v.pad = 0;
+            v.ox = o.origin[0]; v.oy = o.origin[1]; v.oz = o.origin[2];
+            v.dx = o.dimensions[0]; v.dy = o.dimensions[1]; v.dz = o.dimensions[2];
+            v.c = cosf(o.rotateY);   // pR(), hg_sdf.glsl:460-463; host libm so that every
+            v.s = sinf(o.rotateY);   // implementation fed the same op sees the same rotation
+            hops.push_back(v);
+        }
+    }
+    LV(ctx->d_ops.reserve(std::max<size_t>(hops.size(), 1)));
+    LV(ctx->d_touched.reserve(numWords * n));
+    LV(ctx->d_csgCounts.reserve((size_t)8 * n));
+    LV(ctx->h_small.reserve((size_t)8 * n));
+    LV(ctx->d_csgChunks.reserve(n));
+    for (int i = 0; i < n; i++) {
+        FieldEntry &fe = *items[i].fe;
+        CsgChunk &c = hc[i];
+        c.field = fe.d_field;
+        c.touched = ctx->d_touched.p + numWords * i;
+        c.oldKeys = fe.d_keys; c.oldInfo = fe.d_info; c.numOld = fe.numEdges;
+        c.counts = ctx->d_csgCounts.p + 8 * i;
+    }
+    CU(cudaMemcpyAsync(ctx->d_ops.p, hops.data(), hops.size() * sizeof(CsgOpDev), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_csgChunks.p, hc.data(), n * sizeof(CsgChunk), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_touched.p, 0, numWords * n * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, (size_t)8 * n * sizeof(unsigned int), st));
     {
         StageTimer t(ctx, LVN_STAGE_CSG, 2);
-        launch_csg_materials(d, cd, ctx->d_ops.p, numOps, fe.d_field, ctx->d_touched.p, ctx->d_csgCounts.p + 2, st);
-        launch_csg_count(d, fe.d_field, ctx->d_touched.p, fe.d_keys, fe.numEdges, ctx->d_csgCounts.p, st);
+        launch_csg_materials_count(d, ctx->d_csgChunks.p, n, ctx->d_ops.p, st);
     }
-    CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));   // hops must outlive the copy as well
+    CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, (size_t)8 * n * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));   // also: hops / hc must outlive their uploads
     collect_stage_times(ctx);
-    const unsigned int kept = ctx->h_small.p[0], created = ctx->h_small.p[1], changed = ctx->h_small.p[2];
-    if (changed == 0) return LVN_SUCCESS;   // numUpdatedPoints <= 0, compute_csg.cpp:62-66
 
     // When every old edge is invalidated the reference keeps the stale list (numPrunedEdges == 0
     // skips the swap, compute_csg.cpp:160) and ends up with duplicate keys whose winner depends
     // on hash order; here the evident intent: the surviving list is empty.  DESIGN.md "deviations".
-    const unsigned int newE = kept + created;
-    int *newKeys = nullptr;
-    float4 *newInfo = nullptr;
-    if (newE) {
-        CU(cudaMalloc((void **)&newKeys, (size_t)newE * sizeof(int)));
-        CU(cudaMalloc((void **)&newInfo, (size_t)newE * sizeof(float4)));
-        CU(cudaMemsetAsync(ctx->d_csgCounts.p + 4, 0, 2 * sizeof(unsigned int), st));
-        StageTimer t(ctx, LVN_STAGE_CSG, 1);
-        launch_csg_emit(d, cd, ctx->d_ops.p, numOps, fe.d_field, ctx->d_touched.p, fe.d_keys, fe.d_info, fe.numEdges,
-                        (int)kept, newKeys, newInfo, ctx->d_csgCounts.p + 4, st);
+    bool anyEmit = false;
+    for (int i = 0; i < n; i++) {
+        const unsigned int kept = ctx->h_small.p[8 * i + 0], created = ctx->h_small.p[8 * i + 1], changed = ctx->h_small.p[8 * i + 2];
+        CsgChunk &c = hc[i];
+        c.skip = changed == 0;   // numUpdatedPoints <= 0, compute_csg.cpp:62-66
+        c.numKept = (int)kept;
+        if (c.skip) continue;
+        const unsigned int newE = kept + created;
+        if (newE) {
+            CU(cudaMallocAsync((void **)&c.newKeys, (size_t)newE * sizeof(int), st));
+            CU(cudaMallocAsync((void **)&c.newInfo, (size_t)newE * sizeof(float4), st));
+            anyEmit = true;
+        }
     }
+    if (anyEmit) {
+        CU(cudaMemcpyAsync(ctx->d_csgChunks.p, hc.data(), n * sizeof(CsgChunk), cudaMemcpyHostToDevice, st));
+        StageTimer t(ctx, LVN_STAGE_CSG, 1);
+        launch_csg_emit(d, ctx->d_csgChunks.p, n, ctx->d_ops.p, st);
+    }
+    std::vector<FieldEntry *> rebuild;
+    for (int i = 0; i < n; i++) {
+        FieldEntry &fe = *items[i].fe;
+        const CsgChunk &c = hc[i];
+        if (c.skip) {
+            if (fe.numEdges > 0 && !fe.d_table) rebuild.push_back(&fe);   // a fresh entry the edit did not touch
+            continue;
+        }
+        if (fe.d_keys) cudaFreeAsync(fe.d_keys, st);
+        if (fe.d_info) cudaFreeAsync(fe.d_info, st);
+        fe.d_keys = c.newKeys;
+        fe.d_info = c.newInfo;
+        fe.numEdges = (int)(ctx->h_small.p[8 * i + 0] + ctx->h_small.p[8 * i + 1]);
+        rebuild.push_back(&fe);
+    }
+    LV(build_cuckoo_tables(ctx, rebuild));   // its host wait also covers hc's second upload
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     collect_stage_times(ctx);
-    if (fe.d_keys) cudaFree(fe.d_keys);
-    if (fe.d_info) cudaFree(fe.d_info);
-    fe.d_keys = newKeys;
-    fe.d_info = newInfo;
-    fe.numEdges = (int)newE;
-    if (newE) LV(build_cuckoo(ctx, (const unsigned int *)fe.d_keys, newE, &fe.d_table, &fe.prime, fe.params, &fe.cuckooRetries));
     return LVN_SUCCESS;
 }
 
@@ -1211,51 +1279,116 @@ static bool aabb_overlaps(const lvn_aabb &a, const lvn_aabb &b)   // AABB::overl
              a.min[0] > b.max[0] || a.min[1] > b.max[1] || a.min[2] > b.max[2]);
 }
 
-// LoadDensityField, compute_density_field.cpp:235-274.  Returns the cache entry, or nullptr in
-// *out when the chunk is a plain default field that never needs to persist.
-static int load_density_field(lvn_meshgen *ctx, const int32_t min[3], int size, bool forceEntry, FieldEntry **out)
+// LoadDensityField, compute_density_field.cpp:235-274, for n chunks.  out[i] = the cache entry,
+// or nullptr when chunk i is a plain default field that never needs to persist.  Missing entries
+// are materialised in one pass of the path; stored operations overlapping a chunk since its
+// lastCSGOperation are replayed (one ApplyCSGOperations call per chunk, batched over chunks).
+// withTables: entries that were created here and not edited get their hash table too.
+static int load_density_fields(lvn_meshgen *ctx, int n, const int32_t *minSize, bool forceEntry, bool withTables,
+                               std::vector<FieldEntry *> &out)
 {
-    *out = nullptr;
-    const Key key = make_key(min, size);
-    auto it = ctx->fields.find(key);
-    const int startOp = it != ctx->fields.end() ? it->second.lastCSGOperation : 0;
-    lvn_aabb bb;
-    for (int k = 0; k < 3; k++) { bb.min[k] = min[k]; bb.max[k] = min[k] + size; }
-    std::vector<lvn_csg_operation_info> replay;
-    for (size_t i = (size_t)startOp; i < g.storedOps.size(); i++)
-        if (aabb_overlaps(bb, g.storedAABBs[i])) replay.push_back(g.storedOps[i]);
-    if (it == ctx->fields.end()) {
-        if (replay.empty() && !forceEntry) return LVN_SUCCESS;
-        FieldEntry fe;
-        const int rc = materialise_default_field(ctx, min, size, fe);
-        if (rc < 0) { fe.release(); return rc; }
-        it = ctx->fields.emplace(key, fe).first;
+    out.assign(n, nullptr);
+    std::vector<std::vector<lvn_csg_operation_info>> replay(n);
+    std::vector<int> missing;
+    std::vector<int32_t> missingMs;
+    for (int i = 0; i < n; i++) {
+        const int32_t *ms = &minSize[4 * i];
+        auto it = ctx->fields.find(make_key(ms, ms[3]));
+        const int startOp = it != ctx->fields.end() ? it->second.lastCSGOperation : 0;
+        lvn_aabb bb;
+        for (int k = 0; k < 3; k++) { bb.min[k] = ms[k]; bb.max[k] = ms[k] + ms[3]; }
+        for (size_t o = (size_t)startOp; o < g.storedOps.size(); o++)
+            if (aabb_overlaps(bb, g.storedAABBs[o])) replay[i].push_back(g.storedOps[o]);
+        if (it != ctx->fields.end()) { out[i] = &it->second; continue; }
+        if (replay[i].empty() && !forceEntry) continue;
+        bool dup = false;   // the same chunk twice in one list: one entry
+        for (int j : missing) dup = dup || (memcmp(&minSize[4 * j], ms, 4 * sizeof(int32_t)) == 0);
+        if (!dup) { missing.push_back(i); missingMs.insert(missingMs.end(), ms, ms + 4); }
     }
-    FieldEntry &fe = it->second;
-    fe.lastCSGOperation = (int)g.storedOps.size();
-    if (!replay.empty()) LV(apply_csg_to_field(ctx, replay.data(), (int)replay.size(), min, size, fe));
-    *out = &fe;
+    if (!missing.empty()) {
+        std::vector<FieldEntry> fresh;
+        const int rc = materialise_default_fields(ctx, (int)missing.size(), missingMs.data(), fresh);
+        if (rc < 0) { for (FieldEntry &fe : fresh) fe.release(ctx->stream); return rc; }
+        for (size_t k = 0; k < missing.size(); k++) {
+            const int32_t *ms = &minSize[4 * missing[k]];
+            ctx->fields.emplace(make_key(ms, ms[3]), fresh[k]);
+        }
+        for (int i = 0; i < n; i++)
+            if (!out[i] && (!replay[i].empty() || forceEntry)) out[i] = &ctx->fields.find(make_key(&minSize[4 * i], minSize[4 * i + 3]))->second;
+    }
+    std::vector<CsgItem> items;
+    std::vector<FieldEntry *> untouched;
+    for (int i = 0; i < n; i++) {
+        if (!out[i]) continue;
+        FieldEntry &fe = *out[i];
+        fe.lastCSGOperation = (int)g.storedOps.size();
+        if (!replay[i].empty()) {
+            CsgItem it;
+            it.fe = &fe; memcpy(it.ms, &minSize[4 * i], sizeof(it.ms));
+            it.ops = replay[i].data(); it.numOps = (int)replay[i].size();
+            items.push_back(it);
+        } else if (withTables && fe.numEdges > 0 && !fe.d_table) {
+            untouched.push_back(&fe);
+        }
+    }
+    // a chunk listed twice replays once (its replay list was taken before lastCSGOperation moved)
+    {
+        std::vector<CsgItem> uniq;
+        for (const CsgItem &it : items) {
+            bool seen = false;
+            for (const CsgItem &u : uniq) seen = seen || u.fe == it.fe;
+            if (!seen) uniq.push_back(it);
+        }
+        LV(apply_csg_items(ctx, uniq));
+    }
+    if (!untouched.empty()) {
+        std::sort(untouched.begin(), untouched.end());
+        untouched.erase(std::unique(untouched.begin(), untouched.end()), untouched.end());
+        LV(build_cuckoo_tables(ctx, untouched));
+    }
     return LVN_SUCCESS;
 }
 
-extern "C" int lvn_meshgen_apply_csg_operations(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
-                                                const int32_t clipmapNodeMin[3], int clipmapNodeSize)
+static int load_density_field(lvn_meshgen *ctx, const int32_t min[3], int size, bool forceEntry, FieldEntry **out)
 {
-    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
-    if (!ctx || numOps < 0 || (numOps > 0 && !ops)) return LVN_ERR_INVALID_VALUE;
-    FieldEntry *fe = nullptr;
-    LV(load_density_field(ctx, clipmapNodeMin, clipmapNodeSize, true, &fe));
-    LV(apply_csg_to_field(ctx, ops, numOps, clipmapNodeMin, clipmapNodeSize, *fe));
-    fe->lastCSGOperation += numOps;   // compute_csg.cpp:237
+    const int32_t ms[4] = {min[0], min[1], min[2], size};
+    std::vector<FieldEntry *> v;
+    LV(load_density_fields(ctx, 1, ms, forceEntry, true, v));
+    *out = v[0];
     return LVN_SUCCESS;
 }
 
 extern "C" int lvn_meshgen_apply_csg_operations_batch(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
                                                       int nChunks, const int32_t *chunkMinSize)
 {
-    for (int i = 0; i < nChunks; i++)
-        LV(lvn_meshgen_apply_csg_operations(ctx, ops, numOps, &chunkMinSize[4 * i], chunkMinSize[4 * i + 3]));
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (!ctx || numOps < 0 || (numOps > 0 && !ops) || nChunks < 0 || (nChunks > 0 && !chunkMinSize)) return LVN_ERR_INVALID_VALUE;
+    if (nChunks == 0) return LVN_SUCCESS;
+    // Compute_ApplyCSGOperations, compute_csg.cpp:224-242, per chunk: LoadDensityField (create +
+    // replay), ApplyCSGOperations(new ops), lastCSGOperation += numOps
+    std::vector<FieldEntry *> entries;
+    LV(load_density_fields(ctx, nChunks, chunkMinSize, true, numOps == 0, entries));
+    std::vector<CsgItem> items;
+    for (int i = 0; i < nChunks; i++) {
+        bool seen = false;   // the reference would apply the ops twice to a chunk listed twice; so do we, in order
+        for (const CsgItem &u : items) seen = seen || u.fe == entries[i];
+        if (seen) { LV(apply_csg_items(ctx, items)); items.clear(); }
+        CsgItem it;
+        it.fe = entries[i]; memcpy(it.ms, &chunkMinSize[4 * i], sizeof(it.ms));
+        it.ops = ops; it.numOps = numOps;
+        if (numOps > 0) items.push_back(it);
+        entries[i]->lastCSGOperation += numOps;   // compute_csg.cpp:237
+    }
+    LV(apply_csg_items(ctx, items));
     return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_apply_csg_operations(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
+                                                const int32_t clipmapNodeMin[3], int clipmapNodeSize)
+{
+    if (!clipmapNodeMin) return LVN_ERR_INVALID_VALUE;
+    const int32_t ms[4] = {clipmapNodeMin[0], clipmapNodeMin[1], clipmapNodeMin[2], clipmapNodeSize};
+    return lvn_meshgen_apply_csg_operations_batch(ctx, ops, numOps, 1, ms);
 }
 
 extern "C" int lvn_meshgen_free_chunk_octree(lvn_meshgen *ctx, const int32_t min[3], int size)
@@ -1277,10 +1410,12 @@ extern "C" int lvn_meshgen_is_chunk_empty(lvn_meshgen *ctx, const int32_t min[3]
     // default field and store it -- stored CSG operations are NOT replayed on this path
     auto it = ctx->fields.find(make_key(min, size));
     if (it == ctx->fields.end()) {
-        FieldEntry fe;
-        const int rc = materialise_default_field(ctx, min, size, fe);
-        if (rc < 0) { fe.release(); return rc; }
-        it = ctx->fields.emplace(make_key(min, size), fe).first;
+        const int32_t ms[4] = {min[0], min[1], min[2], size};
+        std::vector<FieldEntry> fresh;
+        const int rc = materialise_default_fields(ctx, 1, ms, fresh);
+        if (rc < 0) { for (FieldEntry &fe : fresh) fe.release(ctx->stream); return rc; }
+        it = ctx->fields.emplace(make_key(min, size), fresh[0]).first;
+        LV(build_cuckoo_tables(ctx, std::vector<FieldEntry *>(1, &it->second)));
     }
     *isEmpty = it->second.numEdges == 0;
     return LVN_SUCCESS;

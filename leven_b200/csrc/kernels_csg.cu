@@ -39,23 +39,30 @@ __device__ __forceinline__ int edge_bit_index(int x, int y, int z, int axis, int
     return (x + H * (y + H * z)) * 3 + axis;
 }
 
+// All three kernels are batched: blockIdx.y selects the chunk (CsgChunk), so that an edit that
+// overlaps 27 or 64 chunks is three launches and two host waits, not that many per chunk.
+
 // CSG_HermiteIndices + UpdateFieldMaterials + FindUpdatedEdges in one pass over the field
-__global__ void k_csg_materials(Dims d, ChunkDesc cd, const CsgOpDev *__restrict__ ops, int numOps,
-                                uint8_t *field, unsigned int *touched, unsigned int *numChanged)
+__global__ void k_csg_materials(Dims d, const CsgChunk *__restrict__ chunks, const CsgOpDev *__restrict__ allOps)
 {
+    const CsgChunk cc = chunks[blockIdx.y];
+    const CsgOpDev *ops = allOps + cc.opFirst;
+    uint8_t *field = cc.field;
+    unsigned int *touched = cc.touched;
     const int F = d.F, H = d.H, F3 = F * F * F;
+    unsigned int changed = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F3; i += gridDim.x * blockDim.x) {
         const int x = i % F, y = (i / F) % F, z = i / (F * F);
         const int oldMaterial = field[i];
-        const float wx = (float)(cd.ox + cd.scale * x), wy = (float)(cd.oy + cd.scale * y), wz = (float)(cd.oz + cd.scale * z);
+        const float wx = (float)(cc.ox + cc.scale * x), wy = (float)(cc.oy + cc.scale * y), wz = (float)(cc.oz + cc.scale * z);
         int m = oldMaterial;
-        for (int k = 0; k < numOps; k++) {   // BrushMaterial: the last op with d <= 0 wins
+        for (int k = 0; k < cc.numOps; k++) {   // BrushMaterial: the last op with d <= 0 wins
             const CsgOpDev op = ops[k];
             if (brush_density(wx, wy, wz, op) <= 0.f) m = op.type == 0 ? op.material : LVN_MATERIAL_AIR;
         }
         if (m == oldMaterial) continue;
         field[i] = (uint8_t)m;
-        atomicAdd(numChanged, 1u);
+        changed++;
         const int p[3] = {x, y, z};
         if (x < H && y < H && z < H)
             for (int k = 0; k < 3; k++) {
@@ -71,12 +78,7 @@ __global__ void k_csg_materials(Dims d, ChunkDesc cd, const CsgOpDev *__restrict
             }
         }
     }
-}
-
-void launch_csg_materials(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
-                          uint8_t *field, unsigned int *touchedBits, unsigned int *numChanged, cudaStream_t s)
-{
-    k_csg_materials<<<296, 256, 0, s>>>(d, desc, ops, numOps, field, touchedBits, numChanged);
+    if (changed) atomicAdd(&cc.counts[2], changed);
 }
 
 __device__ __forceinline__ bool edge_sign_change(const uint8_t *__restrict__ field, int F, int x, int y, int z, int axis)
@@ -93,14 +95,16 @@ __device__ __forceinline__ int key_to_bit(int key, const Dims &d)
 }
 
 // counts[0] = old edges that survive the prune; counts[1] = touched edges that now change sign
-__global__ void k_csg_count(Dims d, const uint8_t *__restrict__ field, const unsigned int *__restrict__ touched,
-                            const int *__restrict__ oldKeys, int numOld, unsigned int *counts)
+__global__ void k_csg_count(Dims d, const CsgChunk *__restrict__ chunks)
 {
+    const CsgChunk cc = chunks[blockIdx.y];
+    const uint8_t *field = cc.field;
+    const unsigned int *touched = cc.touched;
     const int H = d.H, numBits = 3 * H * H * H, numWords = (numBits + 31) / 32;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     unsigned int kept = 0, created = 0;
-    for (int i = gid; i < numOld; i += stride) {
-        const int e = key_to_bit(oldKeys[i], d);
+    for (int i = gid; i < cc.numOld; i += stride) {
+        const int e = key_to_bit(cc.oldKeys[i], d);
         if (!((touched[e >> 5] >> (e & 31)) & 1u)) kept++;
     }
     for (int w = gid; w < numWords; w += stride) {
@@ -113,33 +117,30 @@ __global__ void k_csg_count(Dims d, const uint8_t *__restrict__ field, const uns
             if (edge_sign_change(field, d.F, x, y, z, axis)) created++;
         }
     }
-    if (kept) atomicAdd(&counts[0], kept);
-    if (created) atomicAdd(&counts[1], created);
-}
-
-void launch_csg_count(const Dims &d, const uint8_t *field, const unsigned int *touchedBits,
-                      const int *oldKeys, int numOld, unsigned int *counts, cudaStream_t s)
-{
-    k_csg_count<<<148, 256, 0, s>>>(d, field, touchedBits, oldKeys, numOld, counts);
+    if (kept) atomicAdd(&cc.counts[0], kept);
+    if (created) atomicAdd(&cc.counts[1], created);
 }
 
 // PruneFieldEdges + CompactFieldEdges, then the CSG FindEdgeIntersectionInfo for created edges.
-// cursor[0] counts kept edges, cursor[1] created edges (appended after the kept ones: the
-// caller passes newKeys/newInfo and the final kept count is known from k_csg_count).
-__global__ void k_csg_emit(Dims d, ChunkDesc cd, const CsgOpDev *__restrict__ ops, int numOps,
-                           const uint8_t *__restrict__ field, const unsigned int *__restrict__ touched,
-                           const int *__restrict__ oldKeys, const float4 *__restrict__ oldInfo, int numOld,
-                           int numKept, int *__restrict__ newKeys, float4 *__restrict__ newInfo, unsigned int *cursor)
+// counts[4] counts kept edges, counts[5] created edges (appended after the kept ones: the final
+// kept count is known from k_csg_count).
+__global__ void k_csg_emit(Dims d, const CsgChunk *__restrict__ chunks, const CsgOpDev *__restrict__ allOps)
 {
+    const CsgChunk cc = chunks[blockIdx.y];
+    if (cc.skip) return;
+    const CsgOpDev *ops = allOps + cc.opFirst;
+    const int numOps = cc.numOps;
+    const uint8_t *field = cc.field;
+    const unsigned int *touched = cc.touched;
     const int H = d.H, numBits = 3 * H * H * H, numWords = (numBits + 31) / 32;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int i = gid; i < numOld; i += stride) {
-        const int key = oldKeys[i];
+    for (int i = gid; i < cc.numOld; i += stride) {
+        const int key = cc.oldKeys[i];
         const int e = key_to_bit(key, d);
         if ((touched[e >> 5] >> (e & 31)) & 1u) continue;
-        const unsigned int o = atomicAdd(&cursor[0], 1u);
-        newKeys[o] = key;
-        newInfo[o] = oldInfo[i];
+        const unsigned int o = atomicAdd(&cc.counts[4], 1u);
+        cc.newKeys[o] = key;
+        cc.newInfo[o] = cc.oldInfo[i];
     }
     for (int w = gid; w < numWords; w += stride) {
         unsigned int bits = touched[w];
@@ -150,10 +151,10 @@ __global__ void k_csg_emit(Dims d, ChunkDesc cd, const CsgOpDev *__restrict__ op
             const int x = cell % H, y = (cell / H) % H, z = cell / (H * H);
             if (!edge_sign_change(field, d.F, x, y, z, axis)) continue;
             // FindEdgeIntersectionInfo, apply_csg_operation.cl:443-477
-            const int wx = (cd.scale * x) + cd.ox, wy = (cd.scale * y) + cd.oy, wz = (cd.scale * z) + cd.oz;
+            const int wx = (cc.scale * x) + cc.ox, wy = (cc.scale * y) + cc.oy, wz = (cc.scale * z) + cc.oz;
             const float p0x = (float)wx, p0y = (float)wy, p0z = (float)wz;
-            const float p1x = (float)(wx + (axis == 0 ? cd.scale : 0)), p1y = (float)(wy + (axis == 1 ? cd.scale : 0)),
-                        p1z = (float)(wz + (axis == 2 ? cd.scale : 0));
+            const float p1x = (float)(wx + (axis == 0 ? cc.scale : 0)), p1y = (float)(wy + (axis == 1 ? cc.scale : 0)),
+                        p1z = (float)(wz + (axis == 2 ? cc.scale : 0));
             // BrushZeroCrossing: first minimum of |density| over 17 steps x ops
             float minDensity = FLT_MAX, crossing = 0.f;
             for (float t = 0.f; t <= 1.f; t += (1.f / 16.f)) {
@@ -177,20 +178,24 @@ __global__ void k_csg_emit(Dims d, ChunkDesc cd, const CsgOpDev *__restrict__ op
                 normalize3(gx, gy, gz);
                 nx = flip * gx; ny = flip * gy; nz = flip * gz;
             }
-            const unsigned int o = (unsigned int)numKept + atomicAdd(&cursor[1], 1u);
-            newKeys[o] = ((x | (y << d.shift) | (z << (d.shift * 2))) << 2) | axis;
-            newInfo[o] = make_float4(nx, ny, nz, crossing);
+            const unsigned int o = (unsigned int)cc.numKept + atomicAdd(&cc.counts[5], 1u);
+            cc.newKeys[o] = ((x | (y << d.shift) | (z << (d.shift * 2))) << 2) | axis;
+            cc.newInfo[o] = make_float4(nx, ny, nz, crossing);
         }
     }
 }
 
-void launch_csg_emit(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
-                          const uint8_t *field, const unsigned int *touchedBits,
-                          const int *oldKeys, const float4 *oldInfo, int numOld, int numKept,
-                          int *newKeys, float4 *newInfo, unsigned int *cursor, cudaStream_t s)
+void launch_csg_materials_count(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, cudaStream_t s)
 {
-    k_csg_emit<<<148, 256, 0, s>>>(d, desc, ops, numOps, field, touchedBits, oldKeys, oldInfo, numOld,
-                                   numKept, newKeys, newInfo, cursor);
+    if (n <= 0) return;
+    k_csg_materials<<<dim3(296, n), 256, 0, s>>>(d, chunks, ops);
+    k_csg_count<<<dim3(74, n), 256, 0, s>>>(d, chunks);
+}
+
+void launch_csg_emit(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, cudaStream_t s)
+{
+    if (n <= 0) return;
+    k_csg_emit<<<dim3(74, n), 256, 0, s>>>(d, chunks, ops);
 }
 
 }  // namespace lvn

@@ -134,14 +134,23 @@ struct CsgOpDev {          // CSGOperation + host-computed cos/sin of rotateY
     int type, shape, material, pad;
     float ox, oy, oz, dx, dy, dz, c, s;
 };
-void launch_csg_materials(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
-                          uint8_t *field, unsigned int *touchedBits, unsigned int *numChanged, cudaStream_t s);
-void launch_csg_count(const Dims &d, const uint8_t *field, const unsigned int *touchedBits,
-                      const int *oldKeys, int numOld, unsigned int *counts /* kept, created */, cudaStream_t s);
-void launch_csg_emit(const Dims &d, const ChunkDesc &desc, const CsgOpDev *ops, int numOps,
-                     const uint8_t *field, const unsigned int *touchedBits,
-                     const int *oldKeys, const float4 *oldInfo, int numOld, int numKept,
-                     int *newKeys, float4 *newInfo, unsigned int *cursor, cudaStream_t s);
+// one chunk of a batched CSG edit (device-side parameters, blockIdx.y)
+struct CsgChunk {
+    int ox, oy, oz, scale;        // field offset and sample scale (ChunkDesc)
+    uint8_t *field;               // F^3 materials, updated in place
+    unsigned int *touched;        // bitmap over the 3*H^3 Hermite edges: incident to a changed sample
+    const int *oldKeys;           // the field's edge list before the edit
+    const float4 *oldInfo;
+    int numOld;
+    int *newKeys;                 // emit pass: kept edges, then the created ones
+    float4 *newInfo;
+    int numKept;
+    unsigned int *counts;         // [0] kept [1] created [2] changed samples [4] kept cursor [5] created cursor
+    int opFirst, numOps;          // this chunk's slice of the op array
+    int skip;                     // emit pass: nothing changed in this chunk
+};
+void launch_csg_materials_count(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, cudaStream_t s);
+void launch_csg_emit(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, cudaStream_t s);
 
 // ---- launchers (kernels_util.cu) -------------------------------------------
 int  host_find_next_prime(int n);

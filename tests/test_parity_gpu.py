@@ -351,8 +351,12 @@ def test_csg_edit_sequence(lc, oracle_mod, gpu_world, surface_cy):
             assert (lo, hi) == tuple(oracle_mod.csg_operation_bounds(oop))
             touched = [c for c in chunks if not (c[0] + 256 < lo[0] or c[1] + 256 < lo[1] or c[2] + 256 < lo[2] or
                                                  c[0] > hi[0] or c[1] > hi[1] or c[2] > hi[2])]
+            if step % 2 == 0 and touched:
+                # one batched call for every overlapping chunk (lvn_meshgen_apply_csg_operations_batch)
+                assert ctx.applyCSGOperationsBatch([op], np.array([c + [256] for c in touched], np.int32)) == 0
             for c in touched:
-                assert ctx.applyCSGOperations([op], c, 256) == 0
+                if step % 2 == 1:
+                    assert ctx.applyCSGOperations([op], c, 256) == 0
                 world.apply_csg_operations([oop], c, 256)
                 ctx.freeChunkOctree(c, 256)
                 world.free_chunk_octree(c, 256)
