@@ -939,10 +939,25 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 if (hv + c.nodes > out->vertexCapacity || ht + 2 * (int64_t)c.quads > out->triangleCapacity ||
                     hs + c.seams > out->seamCapacity) { hostFull = true; continue; }
                 const ArenaCaps &b = ctx->laneBase[k];
+                // the lane's three arenas in one batched copy: 12 separate memcpys of a 4-lane batch
+                // cost ~55 us more than the same bytes in one (profiles/micro/copy_granularity.cu)
                 cudaStream_t cs = S > 1 ? ctx->copyStream : st;
-                if (c.nodes) CU(cudaMemcpyAsync(out->vertices + hv, ctx->d_vertices.p + b.nodes, (size_t)c.nodes * sizeof(lvn_mesh_vertex), cudaMemcpyDeviceToHost, cs));
-                if (c.quads) CU(cudaMemcpyAsync(out->triangles + ht, ctx->d_tris.p + (size_t)b.quads * 6, (size_t)c.quads * 6 * sizeof(int), cudaMemcpyDeviceToHost, cs));
-                if (c.seams) CU(cudaMemcpyAsync(out->seams + hs, ctx->d_seams.p + b.seams, (size_t)c.seams * sizeof(lvn_seam_node_info), cudaMemcpyDeviceToHost, cs));
+                void *dst[3], *src[3];
+                size_t len[3];
+                size_t m = 0;
+                if (c.nodes) { dst[m] = out->vertices + hv; src[m] = ctx->d_vertices.p + b.nodes; len[m++] = (size_t)c.nodes * sizeof(lvn_mesh_vertex); }
+                if (c.quads) { dst[m] = out->triangles + ht; src[m] = ctx->d_tris.p + (size_t)b.quads * 6; len[m++] = (size_t)c.quads * 6 * sizeof(int); }
+                if (c.seams) { dst[m] = out->seams + hs; src[m] = ctx->d_seams.p + b.seams; len[m++] = (size_t)c.seams * sizeof(lvn_seam_node_info); }
+#if CUDART_VERSION >= 12080
+                if (m > 1) {
+                    cudaMemcpyAttributes attr = {};
+                    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                    size_t attrIdx = 0, failIdx = 0;
+                    if (cudaMemcpyBatchAsync(dst, src, len, m, &attr, &attrIdx, 1, &failIdx, cs) == cudaSuccess) m = 0;
+                    else cudaGetLastError();   // older driver: plain copies below
+                }
+#endif
+                for (size_t i = 0; i < m; i++) CU(cudaMemcpyAsync(dst[i], src[i], len[i], cudaMemcpyDeviceToHost, cs));
                 hv += c.nodes; ht += 2 * (int64_t)c.quads; hs += c.seams;
                 if (ctx->trace) {
                     while (ctx->traceCopyEv.size() < (size_t)S) { cudaEvent_t e; cudaEventCreate(&e); ctx->traceCopyEv.push_back(e); }
