@@ -132,6 +132,7 @@ static DensityParams density_params()
     dp.kind = g.densityKind;
     dp.param = g.densityParam;
     dp.defaultMaterial = g.defaultMaterial;
+    dp.negZero = -0.f;
     return dp;
 }
 

@@ -159,6 +159,136 @@ __device__ __forceinline__ float terrain_height(const float2 *__restrict__ grad,
     return 900.f * terrain(grad, x, z);
 }
 
+// ---------------------------------------------------------------------------
+// Two Terrain evaluations per thread on sm_100's packed FP32 pipe (FADD2 / FMUL2 / FFMA2).
+//
+// The scalar evaluation above is bound by instruction issue: without contraction
+// every flop is its own instruction.  Here a float2 holds the SAME quantity of two independent
+// positions (.x = position A, .y = position B), so one packed instruction does the work of two
+// and each half is the IEEE-754 binary32 round-to-nearest result of the scalar operation --
+// bit-identical to terrain() by construction, and checked against it and the CPU checker in
+// tests/test_parity_gpu.py.
+//
+// What keeps it exact:
+//  * ptxas 12.9 contracts a packed multiply that feeds a packed add into one FFMA2 even for
+//    mul.rn.f32x2 / add.rn.f32x2 under --fmad=false (it never does that to scalar mul.rn.f32).
+//    Every packed product is therefore written as fma(a, b, nz) with nz = (-0, -0) handed in as
+//    a kernel parameter: a*b + (-0) rounds exactly like a*b (and keeps the sign of a zero
+//    product), costs the same single FFMA2, and ptxas cannot fold an addend it does not know.
+//    tests/test_abi.py checks the SASS: no FMUL2 at all in the library.
+//  * floor(v) is fl_rd(v + 1.5*2^23) - 1.5*2^23: exact for |v| < 2^22 (the sum lies in
+//    [2^23, 2^24) where the floats are the integers, rounding down gives floor(v) + 1.5*2^23 and
+//    the subtraction is exact), and the low mantissa bits of the biased sum are floor(v) in two's
+//    complement, which gives the table index without a float->int conversion.
+//  * "t0 < 0 ? 0 : t^4 d" becomes max(t0, 0)^4 d: a culled corner contributes +-0 instead of +0.
+//    x + (-0) == x + (+0) unless every term is -0; a simplex point always has a live corner, and
+//    a live corner that is exactly zero has the same sign in both forms, so only a sum of
+//    (+-0, -0, -0) can differ: -0 here, +0 in the reference.  70*(...) keeps it a zero and every
+//    caller either takes fabsf() or adds it to a running sum that starts at +0 (0 + -0 = +0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 rep2(float v) { return make_float2(v, v); }
+// packed product, uncontractable (see above)
+__device__ __forceinline__ float2 mul2(float2 a, float2 b, float2 nz) { return __ffma2_rn(a, b, nz); }
+
+__device__ __forceinline__ float2 corner2x2(const float2 gA, const float2 gB, float2 x, float2 y, float2 nz)
+{
+    const float2 t0 = sub2(rep2(0.5f), fma2(y, y, mul2(x, x, nz)));
+    const float2 d = make_float2(__fmaf_rn(gA.y, y.x, gA.x * x.x), __fmaf_rn(gB.y, y.y, gB.x * x.y));
+    const float2 tc = make_float2(fmaxf(t0.x, 0.f), fmaxf(t0.y, 0.f));
+    const float2 t = mul2(tc, tc, nz);
+    return mul2(mul2(t, t, nz), d, nz);
+}
+
+__device__ __forceinline__ float2 snoise2x2(const float2 *__restrict__ grad, float2 px, float2 py, float2 nz)
+{
+    const float2 M = rep2(12582912.f);   // 1.5 * 2^23
+    const float2 s = mul2(add2(px, py), rep2(LVN_F2), nz);
+    const float2 mx = __fadd2_rd(add2(px, s), M), my = __fadd2_rd(add2(py, s), M);
+    const float2 ix = sub2(mx, M), iy = sub2(my, M);
+    const float2 t = mul2(add2(ix, iy), rep2(LVN_G2), nz);
+    const float2 x0 = sub2(px, sub2(ix, t)), y0 = sub2(py, sub2(iy, t));
+    const bool xyA = x0.x > y0.x, xyB = x0.y > y0.y;
+    const float2 o1x = make_float2(xyA ? 1.f : 0.f, xyB ? 1.f : 0.f);
+    const float2 o1y = sub2(rep2(1.f), o1x);
+    const float2 *gA = grad + ((__float_as_int(my.x) & 255) * LVN_G2PITCH + (__float_as_int(mx.x) & 255));
+    const float2 *gB = grad + ((__float_as_int(my.y) & 255) * LVN_G2PITCH + (__float_as_int(mx.y) & 255));
+    const float2 g0A = __ldg(gA), g1A = __ldg(gA + (xyA ? 1 : LVN_G2PITCH)), g2A = __ldg(gA + (LVN_G2PITCH + 1));
+    const float2 g0B = __ldg(gB), g1B = __ldg(gB + (xyB ? 1 : LVN_G2PITCH)), g2B = __ldg(gB + (LVN_G2PITCH + 1));
+
+    const float2 n0 = corner2x2(g0A, g0B, x0, y0, nz);
+    const float2 n1 = corner2x2(g1A, g1B, add2(sub2(x0, o1x), rep2(LVN_G2)), add2(sub2(y0, o1y), rep2(LVN_G2)), nz);
+    const float2 n2 = corner2x2(g2A, g2B, sub2(x0, rep2(1.f - 2.f * LVN_G2)), sub2(y0, rep2(1.f - 2.f * LVN_G2)), nz);
+    return mul2(rep2(70.f), add2(add2(n0, n1), n2), nz);
+}
+
+template <int OCTAVES>
+__device__ __forceinline__ float2 basic_fractal_x2(const float2 *__restrict__ grad, float frequency, float lacunarity,
+                                                   float persistence, float2 px, float2 py, float2 nz)
+{
+    float2 noise = rep2(0.f);
+    float amplitude = 1.f;
+    px = mul2(px, rep2(frequency), nz);
+    py = mul2(py, rep2(frequency), nz);
+#pragma unroll
+    for (int i = 0; i < OCTAVES; i++) {
+        noise = add2(noise, mul2(snoise2x2(grad, px, py, nz), rep2(amplitude), nz));
+        px = mul2(px, rep2(lacunarity), nz);
+        py = mul2(py, rep2(lacunarity), nz);
+        amplitude *= persistence;
+    }
+    return noise;
+}
+
+template <int OCTAVES>
+__device__ __forceinline__ float2 ridged_multifractal_x2(const float2 *__restrict__ grad, float lacunarity, float gain,
+                                                         float offset, float2 px, float2 py, float2 nz)
+{
+    float2 signal = snoise2x2(grad, px, py, nz);
+    signal = sub2(rep2(offset), make_float2(fabsf(signal.x), fabsf(signal.y)));
+    signal = mul2(signal, signal, nz);
+    float2 noise = signal;
+    float frequency = 1.f;
+#pragma unroll
+    for (int i = 0; i < OCTAVES; i++) {
+        px = mul2(px, rep2(lacunarity), nz);
+        py = mul2(py, rep2(lacunarity), nz);
+        const float2 weight = make_float2(clamp01(signal.x * gain), clamp01(signal.y * gain));
+        signal = snoise2x2(grad, px, py, nz);
+        signal = sub2(rep2(offset), make_float2(fabsf(signal.x), fabsf(signal.y)));
+        signal = mul2(signal, weight, nz);
+        const float exponent = 1.f / frequency;   // pow(frequency, -1.f)
+        frequency *= lacunarity;
+        noise = add2(noise, mul2(signal, rep2(exponent), nz));
+    }
+    return mul2(noise, rep2(1.f / (float)OCTAVES), nz);
+}
+
+// terrain_height() at (xA, zA) and (xB, zB): x = (xA, xB), z = (zA, zB); negZero must be -0.f
+__device__ __forceinline__ float2 terrain_height_x2(const float2 *__restrict__ grad, float negZero, float2 x, float2 z)
+{
+    const float2 nz = rep2(negZero);
+    const float2 px = mul2(x, rep2(1.f / 2000.f), nz), py = mul2(z, rep2(1.f / 2000.f), nz);
+    const float2 r = ridged_multifractal_x2<7>(grad, 2.114352f, 1.5241f, 1.f, px, py, nz);
+    const float2 bi = basic_fractal_x2<4>(grad, 0.24f, 1.8754f, 0.433f, mul2(px, rep2(-4.33f), nz), mul2(py, rep2(7.98f), nz), nz);
+    const float2 b2 = basic_fractal_x2<2>(grad, 0.63f, 2.2f, 0.15f, px, py, nz);
+    float h[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {   // the tail of Terrain, scalar per position exactly as terrain()
+        const float ridged = clamp01(0.8f * (k ? r.y : r.x));
+        float billow = 0.6f * (k ? bi.y : bi.x);
+        billow = (0.5f * billow) + 0.5f;
+        float noise = billow * ridged;
+        float b = 0.6f * (k ? b2.y : b2.x);
+        b = (b * 0.5f) + 0.5f;
+        noise += b;
+        h[k] = 900.f * noise;
+    }
+    return make_float2(h[0], h[1]);
+}
+
 // BASELINE config 4 stress field: threshold - ridged fBm(snoise3), 4 octaves.
 __device__ __forceinline__ float stress_density(const DensityParams &dp, float x, float y, float z)
 {

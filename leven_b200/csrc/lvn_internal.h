@@ -95,6 +95,7 @@ struct DensityParams {
     int kind;                 // 0 terrain, 1 stress
     float param;              // stress threshold
     int defaultMaterial;
+    float negZero;            // -0.f: the addend of every packed product (density.cuh, terrain_height_x2)
 };
 
 // Optional per-node stage outputs (parity dumps and the octree cache).

@@ -98,3 +98,36 @@ def test_no_device_fails_loudly(built):
     assert lc.Compute_MeshGenContext.create(64).privateCtx_ is None
     assert lc.GetCLErrorString(lc.LVN_ERR_NO_DEVICE) == "LVN_ERR_NO_DEVICE"
     assert lc.FindNextPrime(2048) == 2053        # host-only helper works anywhere
+
+
+def test_packed_fp32_is_not_contracted(built):
+    """Arithmetic spec guard (density.cuh): ptxas contracts a packed FMUL2 feeding an FADD2 into
+    FFMA2 even under --fmad=false, so every packed product is written fma(a, b, -0) with an opaque
+    -0.  The library's SASS must then hold packed adds and fmas but not one FMUL2; every written
+    packed add must still be there (360 per inlined pair evaluation) and at least the written
+    FFMA2s (301 per evaluation: 252 in the 14 snoise2, 49 in the fractals; ptxas may
+    rematerialise a frequency product under register pressure, which repeats the same rounding)."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "leven_b200", "lib", "libleven_b200.so")
+    sass = subprocess.check_output([cuobjdump, "-sass", lib]).decode()
+    assert "FMUL2" not in sass
+    per_fn, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_fn[cur] = {"FFMA2": 0, "FADD2": 0}
+        elif cur:
+            for op in ("FFMA2", "FADD2"):
+                if re.search(r"\b%s\b" % op, line):
+                    per_fn[cur][op] += 1
+    herm = [v for k, v in per_fn.items() if "k_hermite_terrain" in k]
+    cols = [v for k, v in per_fn.items() if "k_columns" in k]
+    assert len(herm) == 1 and len(cols) == 1
+    assert cols[0]["FFMA2"] == 301 and cols[0]["FADD2"] == 360, cols[0]
+    # two inlined evaluations (phase A, phase B)
+    assert herm[0]["FFMA2"] >= 2 * 301 and herm[0]["FADD2"] == 2 * 360, herm[0]
