@@ -60,7 +60,9 @@ __device__ __forceinline__ float corner3(const float4 *__restrict__ grad3, int c
     const int col = __float_as_int(__ldg(&grad3[((cj & 255) << 8) | (ci & 255)]).w);
     const float4 g = __ldg(&grad3[((ck & 255) << 8) | col]);
     const float r = __fmaf_rn(z, z, __fmaf_rn(y, y, x * x));
-    float t = 0.6f - r;
+    // "0.6 - dot(Pf, Pf)": the unsuffixed 0.6 is a double (simplex.cl:184,196,208,220) -- subtract in
+    // double, round once; 0.6f != 0.6 (snoise2's 0.5 is exact either way)
+    float t = (float)(0.6 - (double)r);
     if (t < 0.f) return 0.f;
     t *= t;
     return t * t * __fmaf_rn(g.z, z, __fmaf_rn(g.y, y, g.x * x));

@@ -15,6 +15,13 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+
+/* dot(float4, float4): ONE built-in, one definition -- the same fma chain the simplex
+ * dot products use, for every call site (qef.cl:25-27,149,182). */
+static inline float dot4(float ax, float ay, float az, float aw, float bx, float by, float bz, float bw)
+{
+    return fmaf(aw, bw, fmaf(az, bz, fmaf(ay, by, ax * bx)));
+}
 #endif
 
 #if defined(__x86_64__) && defined(__GNUC__)
@@ -235,7 +242,9 @@ LVO_INLINE float corner3(const lvo_world *w, int ci, int cj, int ck, float x, fl
     const uint8_t perm = texel(w, ci, cj)[3];
     const uint8_t *g = texel(w, perm_col(perm), ck);
     const float gx = unorm_grad(g[0]), gy = unorm_grad(g[1]), gz = unorm_grad(g[2]);
-    float t = 0.6f - fmaf(z, z, fmaf(y, y, x * x));
+    /* "0.6 - dot(Pf, Pf)" (simplex.cl:184,196,208,220): the unsuffixed 0.6 is a double, so the
+     * subtraction happens in double and is rounded once; 0.6f != 0.6, unlike snoise2's 0.5 */
+    float t = (float)(0.6 - (double)fmaf(z, z, fmaf(y, y, x * x)));
     if (t < 0.f) return 0.f;
     t *= t;
     return t * t * fmaf(gz, z, fmaf(gy, y, gx * x));
@@ -896,7 +905,7 @@ static void qef_add_point(lvo_qef *qef, lvo_f4 n, lvo_f4 p)   /* qef.cl:170-191 
     qef->ATA[3] += n.y * n.y;
     qef->ATA[4] += n.y * n.z;
     qef->ATA[5] += n.z * n.z;
-    b = ((p.x * n.x + p.y * n.y) + p.z * n.z) + p.w * n.w;   /* dot(float4) */
+    b = dot4(p.x, p.y, p.z, p.w, n.x, n.y, n.z, n.w);
     qef->ATb.x += n.x * b;
     qef->ATb.y += n.y * b;
     qef->ATb.z += n.z * b;
@@ -1037,7 +1046,7 @@ static float svd_invdet(float x, float tol)   /* qef.cl:107-109 (double 1.0/x, s
 
 static void svd_vmul_sym(lvo_f4 *result, const float A[6], lvo_f4 v)   /* qef.cl:146-152 */
 {
-    result->x = ((A[0] * v.x + A[1] * v.y) + A[2] * v.z) + 0.f * v.w;
+    result->x = dot4(A[0], A[1], A[2], 0.f, v.x, v.y, v.z, v.w);   /* the x row is written with dot(), y and z are not */
     result->y = A[1] * v.x + A[3] * v.y + A[4] * v.z;
     result->z = A[2] * v.x + A[4] * v.y + A[5] * v.z;
 }
@@ -1065,9 +1074,9 @@ static void svd_solve_ATA_ATb(const float ATA[6], lvo_f4 ATb, lvo_f4 *x)   /* qe
                 o[r][c] = V[r][0] * d0 * V[c][0] + V[r][1] * d1 * V[c][1] + V[r][2] * d2 * V[c][2];
     }
     /* svd_mul_matrix_vec, qef.cl:23-29 */
-    x->x = ((o[0][0] * ATb.x + o[0][1] * ATb.y) + o[0][2] * ATb.z) + 0.f * ATb.w;
-    x->y = ((o[1][0] * ATb.x + o[1][1] * ATb.y) + o[1][2] * ATb.z) + 0.f * ATb.w;
-    x->z = ((o[2][0] * ATb.x + o[2][1] * ATb.y) + o[2][2] * ATb.z) + 0.f * ATb.w;
+    x->x = dot4(o[0][0], o[0][1], o[0][2], 0.f, ATb.x, ATb.y, ATb.z, ATb.w);
+    x->y = dot4(o[1][0], o[1][1], o[1][2], 0.f, ATb.x, ATb.y, ATb.z, ATb.w);
+    x->z = dot4(o[2][0], o[2][1], o[2][2], 0.f, ATb.x, ATb.y, ATb.z, ATb.w);
     x->w = 0.f;
 }
 

@@ -1,0 +1,353 @@
+"""oracle/ref.py -- drive the reference's own OpenCL C kernels, compiled for the host CPU
+(oracle/_ref/libleven_cl_ref.so, built by `make -C oracle ref` from /root/reference/leven/cl).
+
+TEST INFRASTRUCTURE: used to pin the C restatement (oracle/lvn_oracle.c) and to generate the
+golden vectors under tests/golden/ (tests/golden/gen_ref_vectors.py).  Only tests/, smoke() and
+bench.py's CPU-baseline legs may import this module; the product (leven_b200/) never does.
+
+The kernels are the reference's text.  What is restated HERE is the host orchestration that
+strings them together -- which kernel, which arguments, which NDRange, which scan between --
+following the reference host files line by line:
+    GenerateDefaultDensityField / FindDefaultEdges   leven/src/compute_density_field.cpp:138-231
+    ConstructOctreeFromField                          leven/src/compute_octree.cpp:25-150
+    GenerateMeshFromOctree                            leven/src/compute_octree.cpp:189-271
+    GatherSeamNodesFromOctree                         leven/src/compute_octree.cpp:275-322
+    Cuckoo_InitialiseTable / Cuckoo_InsertKeys        leven/src/compute_cuckoo.cpp:49-138
+    ExclusiveScan (scan.cl needs work-group barriers; it computes a plain exclusive prefix sum
+    and returns data[n-1] + scan[n-1])                leven/src/compute.cpp:328-420
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libleven_cl_ref.so")
+REFERENCE_CL = "/root/reference/leven/cl"
+
+LEAF_SIZE_SCALE = 4
+CLIPMAP_LEAF_SIZE = 256
+CUCKOO_EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
+MIN_TABLE_SIZE = 2048            # compute_cuckoo.cpp:16
+
+SEAM_DTYPE = np.dtype([("localspaceMin", np.int32, 4), ("position", np.float32, 4), ("normal", np.float32, 4)])
+VERTEX_DTYPE = np.dtype([("xyz", np.float32, 4), ("normal", np.float32, 4), ("colour", np.float32, 4)])
+QEF_DTYPE = np.dtype([("ATA", np.float32, 6), ("pad", np.float32, 2), ("ATb", np.float32, 4), ("masspoint", np.float32, 4)])
+CSG_DTYPE = np.dtype([("type", np.int32), ("brushShape", np.int32), ("material", np.int32), ("rotateY", np.float32),
+                      ("origin", np.float32, 4), ("dimensions", np.float32, 4)])
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def build(force=False):
+    """compile the reference kernels where they lie; a no-op (returns False) when /root/reference is absent"""
+    if not os.path.isdir(REFERENCE_CL):
+        return available()
+    deps = [os.path.join(_HERE, "ref_shim", f) for f in ("ref_kernels.cpp", "clc.hpp", "translate.py")]
+    if force or not available() or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+        env = dict(os.environ)
+        env.pop("CC", None); env.pop("CXX", None)
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "ref"], env=env)
+    return True
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise ImportError(f"{LIB_PATH} is missing: `make -C oracle ref` (needs /root/reference)")
+        L = C.CDLL(LIB_PATH)
+        L.ref_DensityFunc.restype = C.c_float
+        L.ref_DensityFunc.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+        L.ref_snoise2.restype = C.c_float
+        L.ref_snoise2.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.ref_snoise3.restype = C.c_float
+        L.ref_snoise3.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+        L.ref_Cuckoo_Find.restype = C.c_uint32
+        L.ref_Cuckoo_Hash.restype = C.c_uint32
+        assert L.ref_voxels_per_chunk() == 64
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i4(v):
+    return np.array([int(v[0]), int(v[1]), int(v[2]), 0], np.int32)
+
+
+def exclusive_scan(data):
+    """compute.cpp:328-420: scan[i] = sum(data[:i]); returns (scan, data[n-1] + scan[n-1])"""
+    data = np.asarray(data, np.int32)
+    scan = np.zeros(len(data), np.int32)
+    if len(data):
+        np.cumsum(data[:-1], out=scan[1:])
+    total = int(data[-1] + scan[-1]) if len(data) else 0
+    return scan, total
+
+
+def find_next_prime(n):
+    """primes.cpp: smallest prime >= n"""
+    def is_prime(k):
+        if k < 2:
+            return False
+        i = 2
+        while i * i <= k:
+            if k % i == 0:
+                return False
+            i += 1
+        return True
+    while not is_prime(n):
+        n += 1
+    return n
+
+
+def colour_for_min_leaf_size(min_leaf_size):
+    """ColourForMinLeafSize, clipmap.cpp:329-352"""
+    table = {1: (0.3, 0.1, 0.0), 2: (0.0, 0.0, 0.5), 4: (0.0, 0.5, 0.5), 8: (0.5, 0.0, 0.5), 16: (0.0, 0.5, 0.0)}
+    return table.get(int(min_leaf_size), (0.5, 0.0, 0.0))
+
+
+class Cuckoo:
+    """CuckooData + Cuckoo_InitialiseTable + Cuckoo_InsertKeys (compute_cuckoo.cpp:49-138).  The hash
+    parameters come from std::mt19937 + uniform_int_distribution there (implementation-defined,
+    unobservable); here numpy's generator draws from the same range [2^15, 2^30]."""
+    _rng = np.random.default_rng(5489)
+
+    def __init__(self, count):
+        self.prime = find_next_prime(max(MIN_TABLE_SIZE, 2 * int(count)))
+        self.table = np.full(self.prime, CUCKOO_EMPTY, np.uint64)
+        # the reference's stash has 101 entries but is indexed mod prime (cuckoo.cl:67-69): give it room
+        self.stash = np.full(self.prime, CUCKOO_EMPTY, np.uint64)
+        self.params = self._draw()
+        self.stash_used = 0
+        self.retries = 0
+
+    def _draw(self):
+        return self._rng.integers(1 << 15, (1 << 30) + 1, size=10, dtype=np.uint32)
+
+    def insert_keys(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        n = len(keys)
+        inserted = np.zeros(n, np.int32)
+        stash_used = np.zeros(n, np.int32)
+        inserted_count = 0
+        while True:
+            if inserted_count > 0:
+                self.retries += 1
+                self.params = self._draw()
+                self.table[:] = CUCKOO_EMPTY
+                self.stash[:] = CUCKOO_EMPTY
+            lib().ref_Cuckoo_InsertKeys(n, _p(keys), _p(self.table), _p(self.stash), C.c_uint32(self.prime),
+                                        _p(self.params), _p(inserted), _p(stash_used))
+            _, inserted_count = exclusive_scan(inserted)
+            _, stash_count = exclusive_scan(stash_used)
+            if inserted_count >= n:
+                break
+            if self.retries > 64:
+                raise RuntimeError("cuckoo insert does not converge")
+        self.stash_used |= int(stash_count != 0)
+
+    def find(self, key):
+        return lib().ref_Cuckoo_Find(C.c_uint32(int(key)), _p(self.table), _p(self.stash), C.c_uint32(self.prime),
+                                     _p(self.params), int(self.stash_used))
+
+
+class RefWorld:
+    """The reference pipeline for one chunk, kernels from the reference text, V = 64."""
+    V, H, F = 64, 65, 66
+
+    def __init__(self, image, default_material=0):
+        self.L = lib()
+        self.image = np.ascontiguousarray(image, np.uint8)
+        assert self.image.size == 256 * 256 * 4
+        self.default_material = int(default_material)
+
+    def density(self, x, y, z):
+        return self.L.ref_DensityFunc(_p(self.image), x, y, z)
+
+    def snoise2(self, x, y):
+        return self.L.ref_snoise2(_p(self.image), x, y)
+
+    def snoise3(self, x, y, z):
+        return self.L.ref_snoise3(_p(self.image), x, y, z)
+
+    # ---- compute_density_field.cpp:138-161 ----
+    def generate_field(self, mn, size):
+        off = _i4([m // LEAF_SIZE_SCALE for m in mn])          # LeafScaleVec(field->min)
+        sample_scale = size // (self.V * LEAF_SIZE_SCALE)
+        field = np.zeros(self.F ** 3, np.int32)
+        self.L.ref_GenerateDefaultField(_p(self.image), _p(off), sample_scale, self.default_material, _p(field))
+        return field
+
+    # ---- compute_density_field.cpp:165-231 ----
+    def find_edges(self, mn, size, materials):
+        off = _i4([m // LEAF_SIZE_SCALE for m in mn])
+        n = 3 * self.H ** 3
+        occupancy = np.zeros(n, np.int32)
+        indices = np.zeros(n, np.int32)
+        self.L.ref_FindFieldEdges(_p(off), _p(materials), _p(occupancy), _p(indices))
+        scan, num_edges = exclusive_scan(occupancy)
+        if num_edges == 0:
+            return np.zeros(0, np.int32), np.zeros((0, 4), np.float32)
+        compact = np.zeros(num_edges, np.int32)
+        self.L.ref_CompactEdges(n, _p(occupancy), _p(scan), _p(indices), _p(compact))
+        info = np.zeros((num_edges, 4), np.float32)
+        sample_scale = size // (self.V * LEAF_SIZE_SCALE)
+        self.L.ref_FindEdgeIntersectionInfo(_p(self.image), _p(off), sample_scale, num_edges, _p(compact), _p(info))
+        return compact, info
+
+    # ---- compute_octree.cpp:25-150 ----
+    def construct_octree(self, mn, size, materials, edge_keys, edge_info):
+        n3 = self.V ** 3
+        occ = np.zeros(n3, np.int32); einfo = np.zeros(n3, np.int32)
+        codes = np.zeros(n3, np.int32); mats = np.zeros(n3, np.int32)
+        self.L.ref_FindActiveVoxels(_p(materials), _p(occ), _p(einfo), _p(codes), _p(mats))
+        scan, num_nodes = exclusive_scan(occ)
+        if num_nodes <= 0:
+            return None
+        c_codes = np.zeros(num_nodes, np.int32); c_einfo = np.zeros(num_nodes, np.int32); c_mats = np.zeros(num_nodes, np.int32)
+        self.L.ref_CompactVoxels(n3, _p(occ), _p(einfo), _p(codes), _p(mats), _p(scan), _p(c_codes), _p(c_einfo), _p(c_mats))
+        edge_table = Cuckoo(len(edge_keys))
+        edge_table.insert_keys(edge_keys)
+        sample_scale = size // (self.V * LEAF_SIZE_SCALE)
+        normals = np.zeros((num_nodes, 4), np.float32)
+        qefs = np.zeros(num_nodes, QEF_DTYPE)
+        edge_info = np.ascontiguousarray(edge_info, np.float32)
+        self.L.ref_CreateLeafNodes(num_nodes, sample_scale, _p(c_codes), _p(c_einfo), _p(edge_info), _p(normals), _p(qefs),
+                                   _p(edge_table.table), _p(edge_table.stash), C.c_uint32(edge_table.prime),
+                                   _p(edge_table.params), int(edge_table.stash_used))
+        positions = np.zeros((num_nodes, 4), np.float32)
+        wso = np.array([mn[0], mn[1], mn[2], 0], np.float32)
+        self.L.ref_SolveQEFs(num_nodes, _p(wso), _p(qefs), _p(positions))
+        node_table = Cuckoo(num_nodes)
+        node_table.insert_keys(c_codes.view(np.uint32))
+        return dict(numNodes=num_nodes, codes=c_codes.view(np.uint32), edgeMasks=c_einfo, matWords=c_mats, qefs=qefs,
+                    positions=positions, normals=normals, table=node_table, edgeTable=edge_table)
+
+    # ---- compute_octree.cpp:189-271 ----
+    def generate_mesh(self, size, octree):
+        n = octree["numNodes"]
+        index_buffer = np.zeros(n * 18, np.int32)
+        tri_valid = np.zeros(n * 3, np.int32)
+        t = octree["table"]
+        self.L.ref_GenerateMesh(n, _p(octree["codes"]), _p(octree["matWords"]), _p(index_buffer), _p(tri_valid),
+                                _p(t.table), _p(t.stash), C.c_uint32(t.prime), _p(t.params), int(t.stash_used))
+        scan, num_quads = exclusive_scan(tri_valid)
+        compact = np.zeros(max(num_quads, 0) * 6, np.int32)
+        if num_quads > 0:
+            self.L.ref_CompactMeshTriangles(n * 3, _p(tri_valid), _p(scan), _p(index_buffer), _p(compact))
+        colour = np.array(list(colour_for_min_leaf_size(size // CLIPMAP_LEAF_SIZE)) + [0.0], np.float32)
+        vertices = np.zeros(n, VERTEX_DTYPE)
+        self.L.ref_GenerateMeshVertexBuffer(n, _p(octree["positions"]), _p(octree["normals"]), _p(octree["matWords"]),
+                                            _p(colour), _p(vertices))
+        return vertices, compact.reshape(-1, 3)
+
+    # ---- compute_octree.cpp:275-322 ----
+    def gather_seam_nodes(self, octree):
+        n = octree["numNodes"]
+        is_seam = np.zeros(n, np.int32)
+        self.L.ref_FindSeamNodes(n, _p(octree["codes"]), _p(is_seam))
+        scan, num = exclusive_scan(is_seam)
+        out = np.zeros(max(num, 0), SEAM_DTYPE)
+        if num > 0:
+            self.L.ref_ExtractSeamNodeInfo(n, _p(is_seam), _p(scan), _p(octree["codes"]), _p(octree["matWords"]),
+                                           _p(octree["positions"]), _p(octree["normals"]), _p(out))
+        return out
+
+    # ---- Compute_GenerateChunkMesh, compute_octree.cpp:351-375 (no caches: one fresh chunk) ----
+    def generate_chunk_mesh(self, mn, size):
+        materials = self.generate_field(mn, size)
+        keys, info = self.find_edges(mn, size, materials)
+        out = dict(materials=materials, edgeKeys=keys, edgeInfo=info, numEdges=len(keys), numNodes=0, numTriangles=0,
+                   numSeamNodes=0)
+        if len(keys) == 0:
+            return out
+        octree = self.construct_octree(mn, size, materials, keys, info)
+        if octree is None:
+            return out
+        vertices, tris = self.generate_mesh(size, octree)
+        seams = self.gather_seam_nodes(octree)
+        out.update(numNodes=octree["numNodes"], numTriangles=len(tris), numSeamNodes=len(seams),
+                   codes=octree["codes"], edgeMasks=octree["edgeMasks"], matWords=octree["matWords"], qefs=octree["qefs"],
+                   positions=octree["positions"], normals=octree["normals"], vertices=vertices, indices=tris, seams=seams,
+                   cuckooRetries=octree["table"].retries + octree["edgeTable"].retries)
+        return out
+
+    # ---- apply_csg_operation.cl, kernel by kernel (compute_csg.cpp:11-220 strings them together) ----
+    def csg_materials(self, mn, size, ops, materials):
+        """CSG_HermiteIndices over the whole field: (updated flags, positions, new materials)"""
+        off = _i4([m // LEAF_SIZE_SCALE for m in mn])
+        sample_scale = size // (self.V * LEAF_SIZE_SCALE)
+        ops = np.ascontiguousarray(ops, CSG_DTYPE)
+        n = self.F ** 3
+        updated = np.zeros(n, np.int32); positions = np.zeros((n, 4), np.int32); new_mats = np.zeros(n, np.int32)
+        self.L.ref_CSG_HermiteIndices(_p(off), len(ops), _p(ops), sample_scale, _p(np.ascontiguousarray(materials, np.int32)),
+                                      _p(updated), _p(positions), _p(new_mats))
+        return updated, positions, new_mats
+
+    def csg_updated_edges(self, positions):
+        positions = np.ascontiguousarray(positions, np.int32).reshape(-1, 4)
+        out = np.zeros(len(positions) * 6, np.int32)
+        self.L.ref_CSG_FindUpdatedEdges(len(positions), _p(positions), _p(out))
+        return out
+
+    def csg_filter_valid_edges(self, edge_indices, materials):
+        edge_indices = np.ascontiguousarray(edge_indices, np.int32)
+        valid = np.zeros(len(edge_indices), np.int32)
+        self.L.ref_CSG_FilterValidEdges(len(edge_indices), _p(edge_indices), _p(np.ascontiguousarray(materials, np.int32)), _p(valid))
+        return valid
+
+    def csg_edge_info(self, mn, size, ops, edge_keys):
+        off = _i4([m // LEAF_SIZE_SCALE for m in mn])
+        sample_scale = size // (self.V * LEAF_SIZE_SCALE)
+        ops = np.ascontiguousarray(ops, CSG_DTYPE)
+        edge_keys = np.ascontiguousarray(edge_keys, np.int32)
+        out = np.zeros((len(edge_keys), 4), np.float32)
+        self.L.ref_CSG_FindEdgeIntersectionInfo(_p(off), len(ops), _p(ops), sample_scale, len(edge_keys), _p(edge_keys), _p(out))
+        return out
+
+    def apply_csg(self, mn, size, ops, materials, edge_keys, edge_info):
+        """ApplyCSGOperations, compute_csg.cpp:11-220, on one field (materials, edge list):
+        returns the edited (materials, edge_keys, edge_info).  The scans, compactions and
+        RemoveDuplicates between the kernels are numpy (their results are defined: stable
+        compaction, set of unique keys -- np.unique gives the set in ascending order, the
+        reference's hash order is arbitrary); PruneFieldEdges' O(E*K) membership loop is np.isin."""
+        materials = np.array(materials, np.int32)
+        edge_keys = np.asarray(edge_keys, np.int32)
+        edge_info = np.asarray(edge_info, np.float32).reshape(-1, 4)
+        if len(ops) == 0:
+            return materials, edge_keys, edge_info
+        updated, positions, new_mats = self.csg_materials(mn, size, ops, materials)
+        sel = np.nonzero(updated)[0]
+        if len(sel) == 0:
+            return materials, edge_keys, edge_info
+        pts = positions[sel]                                   # CompactPoints
+        F = self.F
+        materials[pts[:, 0] + F * pts[:, 1] + F * F * pts[:, 2]] = new_mats[sel]   # UpdateFieldMaterials
+        gen = self.csg_updated_edges(pts)
+        gen = gen[gen != -1]                                   # RemoveInvalidIndices + CompactIndexArray
+        invalidated = np.unique(gen)                           # RemoveDuplicates
+        # FilterValidEdges reads one sample past the grid for edges that start at index F-1 (the
+        # reference does the same read on the device): pad the field so the read stays in bounds
+        padded = np.concatenate([materials, np.full(F * F + F + 2, 201, np.int32)])
+        valid = self.csg_filter_valid_edges(invalidated, padded)
+        created = invalidated[valid != 0]
+        if len(invalidated) and len(edge_keys):                # PruneFieldEdges + CompactFieldEdges
+            keep = ~np.isin(edge_keys, invalidated)
+            if keep.sum() > 0:                                 # compute_csg.cpp:160: no swap when nothing survives
+                edge_keys, edge_info = edge_keys[keep], edge_info[keep]
+        if len(created):
+            info = self.csg_edge_info(mn, size, ops, created)
+            if len(edge_keys):
+                edge_keys = np.concatenate([edge_keys, created]); edge_info = np.concatenate([edge_info, info])
+            else:
+                edge_keys, edge_info = created, info
+        return materials, edge_keys, edge_info

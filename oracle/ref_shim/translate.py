@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Make one of the reference's OpenCL C sources palatable to g++ (with clc.hpp), without changing
+what it computes.  Usage: translate.py <in.cl> <out.inc>
+
+Only syntax that C++ cannot parse is rewritten; every expression, table and constant stays the
+reference's own text (a #line directive points compiler diagnostics back at it):
+  (float4)(a, b, c, d)   ->  float4(a, b, c, d)        OpenCL vector literal -> constructor call
+  #include "cl/x.glsl"   ->  #include "x.glsl.inc"     the translated copy next to this one
+  #pragma OPENCL / unroll ->  dropped
+The output is a build intermediate under oracle/_ref/ (git-ignored, deleted after the build).
+"""
+import os
+import re
+import sys
+
+
+def translate(text, src_path):
+    text = re.sub(r"\(\s*(float|int|uint)([234])\s*\)\s*\(", r"\1\2(", text)
+    text = re.sub(r'#include\s+"cl/([A-Za-z0-9_.]+)"', r'#include "\1.inc"', text)
+    text = re.sub(r"^\s*#pragma\s+(OPENCL|unroll).*$", "", text, flags=re.M)
+    return '#line 1 "%s"\n%s\n' % (src_path, text)
+
+
+if __name__ == "__main__":
+    src, dst = sys.argv[1], sys.argv[2]
+    with open(src, encoding="utf-8", errors="replace") as f:
+        out = translate(f.read(), os.path.abspath(src))
+    with open(dst, "w") as f:
+        f.write(out)

@@ -1,0 +1,293 @@
+"""The pin: outputs of the REFERENCE's own kernel text (leven/cl/*.cl compiled for the host through
+oracle/ref_shim, driven by oracle/ref.py) against (a) the C restatement the GPU parity tests use
+as their checker and (b) the CUDA path itself.
+
+  * tests/golden/ref_chunks.npz was generated from the reference kernels by
+    tests/golden/gen_ref_vectors.py; it travels, /root/reference does not.
+  * where oracle/_ref/libleven_cl_ref.so exists (it is built in the container that holds
+    /root/reference and shipped with the snapshot), the live tests run the reference kernels on
+    fresh inputs as well.
+
+Bit-exact everywhere (the shim's built-ins and the oracle share one arithmetic spec);
+the QEF records' two pad floats are uninitialised in the reference and are excluded."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SEED
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_chunks.npz")
+STAGES = ("materials", "edgeKeys", "edgeInfo", "codes", "edgeMasks", "matWords", "qefs", "positions", "normals",
+          "vertices", "indices", "seams")
+COUNTS = ("numEdges", "numNodes", "numTriangles", "numSeamNodes")
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.fixture(scope="module")
+def ref_mod(built):
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libleven_cl_ref.so not built (needs /root/reference)")
+    return R
+
+
+def beq(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
+def zero_pad(q):
+    q = q.copy()
+    if len(q):
+        q["pad"] = 0
+    return q
+
+
+def oracle_csg_ops(oracle_mod, ops):
+    return [oracle_mod.make_csg_op(int(o["type"]), int(o["brushShape"]), int(o["material"]), o["origin"][:3],
+                                   o["dimensions"][:3], float(o["rotateY"])) for o in ops]
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle vs golden vectors (runs everywhere)
+# ---------------------------------------------------------------------------------------------
+def test_noise_image_is_the_fixture_input(oracle_mod, golden):
+    assert digest(oracle_mod.noise_image(SEED)) == str(golden["image_sha256"])
+    assert int(golden["seed"]) == SEED
+
+
+def test_oracle_equals_reference_kernels_origin_chunk(world, golden, surface_cy):
+    """BASELINE config 1, every stage array of the reference run"""
+    assert int(golden["cy0"]) == surface_cy
+    mn = [int(v) for v in golden["origin/min_size"][:3]]
+    o = world.generate_chunk_mesh(mn, 256)
+    world.free_chunk_octree(mn, 256)
+    for k in COUNTS:
+        assert o[k] == int(golden[f"origin/{k}"]), k
+    assert np.array_equal(o["materials"], golden["origin/materials_u8"].astype(np.int32))
+    for k in STAGES[1:]:
+        want = golden[f"origin/{k}"]
+        got = zero_pad(o[k]) if k == "qefs" else o[k]
+        assert beq(got, want), f"stage {k} differs from the reference kernels' output"
+
+
+def test_oracle_equals_reference_kernels_digest_cases(world, golden):
+    """ring / world-corner / LOD1 / LOD2 / empty chunks: sha256 of every stage array"""
+    stages = [str(s) for s in golden["stages"]]
+    assert tuple(stages) == STAGES
+    for name in golden["digest_cases"]:
+        name = str(name)
+        ms = [int(v) for v in golden[f"d/{name}/min_size"]]
+        o = world.generate_chunk_mesh(ms[:3], ms[3])
+        world.free_chunk_octree(ms[:3], ms[3])
+        assert [o[k] for k in COUNTS] == [int(v) for v in golden[f"d/{name}/counts"]], name
+        for k, want in zip(STAGES, golden[f"d/{name}/sha256"]):
+            got = zero_pad(o[k]) if k == "qefs" else o[k]
+            assert digest(got) == str(want), f"{name}: stage {k}"
+
+
+def test_oracle_equals_reference_kernels_csg(oracle_mod, golden):
+    """the CSG kernels (apply_csg_operation.cl) on the origin chunk, then the mesh of the edited field"""
+    w = oracle_mod.World(seed=SEED, default_material=0, voxels_per_chunk=64)
+    try:
+        mn = [int(v) for v in golden["origin/min_size"][:3]]
+        w.apply_csg_operations(oracle_csg_ops(oracle_mod, golden["csg/ops"]), mn, 256)
+        o = w.generate_chunk_mesh(mn, 256)
+        assert np.array_equal(o["materials"], golden["csg/materials_u8"].astype(np.int32))
+        order = np.argsort(o["edgeKeys"], kind="stable")
+        assert np.array_equal(o["edgeKeys"][order], golden["csg/edgeKeys_sorted"])
+        assert beq(o["edgeInfo"][order], golden["csg/edgeInfo_sorted"])
+        for k, gk in (("codes", "codes"), ("matWords", "matWords"), ("positions", "positions"), ("normals", "normals"),
+                      ("indices", "indices"), ("seams", "seams")):
+            assert beq(o[k], golden[f"csg/{gk}"]), k
+        assert digest(o["vertices"]) == str(golden["csg/vertices_sha256"])
+    finally:
+        w.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle vs the live reference kernels (where oracle/_ref is built)
+# ---------------------------------------------------------------------------------------------
+def test_live_noise_functions(world, ref_mod):
+    rw = ref_mod.RefWorld(world.image)
+    rng = np.random.default_rng(7)
+    for _ in range(3000):
+        x, y, z = (np.float32(v) for v in rng.uniform(-4000, 4000, 3))
+        assert np.float32(world.snoise2(x / 9, y / 9)).tobytes() == np.float32(rw.snoise2(x / 9, y / 9)).tobytes()
+        assert np.float32(world.snoise3(x / 33, y / 33, z / 33)).tobytes() == np.float32(rw.snoise3(x / 33, y / 33, z / 33)).tobytes()
+        assert np.float32(world.density(x, y, z)).tobytes() == np.float32(rw.density(x, y, z)).tobytes()
+    # lattice points and the world origin: exact zeros, ties in the simplex selection
+    for x, z in ((0.0, 0.0), (2000.0, 0.0), (-2000.0, 2000.0), (1.0, -1.0), (64.0, 64.0)):
+        assert np.float32(world.density(x, 0.0, z)).tobytes() == np.float32(rw.density(x, 0.0, z)).tobytes()
+
+
+def test_live_random_chunks(world, ref_mod, surface_cy):
+    rw = ref_mod.RefWorld(world.image)
+    rng = np.random.default_rng(2024)
+    done = 0
+    for _ in range(40):
+        cx, cz = (int(v) for v in rng.integers(-8, 8, 2))
+        size = int(rng.choice([256, 256, 512]))
+        h = -rw.density(np.float32(cx * 64.0 + 32), np.float32(0.0), np.float32(cz * 64.0 + 32))
+        cy = int(h * 4 // size)
+        mn = [cx * 256 // size * size, cy * size, cz * 256 // size * size]
+        r = rw.generate_chunk_mesh(mn, size)
+        o = world.generate_chunk_mesh(mn, size)
+        world.free_chunk_octree(mn, size)
+        for k in COUNTS:
+            assert o[k] == r[k], (mn, size, k)
+        if r["numNodes"] == 0:
+            continue
+        for k in STAGES:
+            a, b = (zero_pad(o[k]), zero_pad(r[k])) if k == "qefs" else (o[k], r[k])
+            assert beq(a, b), (mn, size, k)
+        done += 1
+        if done >= 6:
+            break
+    assert done >= 4
+
+
+def test_live_csg_random_scripts(oracle_mod, ref_mod, surface_cy):
+    image = oracle_mod.noise_image(SEED)
+    rw = ref_mod.RefWorld(image)
+    rng = np.random.default_rng(99)
+    mn = [256, surface_cy * 256, -256]
+    for trial in range(3):
+        w = oracle_mod.World(image=image, default_material=0, voxels_per_chunk=64)
+        try:
+            base = w.generate_chunk_mesh(mn, 256)
+            w.free_chunk_octree(mn, 256)
+            n = int(rng.integers(1, 5))
+            ops = np.zeros(n, ref_mod.CSG_DTYPE)
+            for i in range(n):
+                add = bool(rng.integers(0, 2))
+                org = [mn[0] / 4 + float(rng.integers(-2, 67)) + 0.5, surface_cy * 64 + float(rng.integers(0, 64)) + 0.5,
+                       mn[2] / 4 + float(rng.integers(-2, 67)) + 0.5]
+                dim = [float(rng.integers(1, 14)) for _ in range(3)]
+                ops[i] = (0 if add else 1, int(rng.integers(0, 2)), int(rng.integers(1, 5)) if add else 201,
+                          float(rng.uniform(-1.5, 1.5)) if trial else 0.0, org + [0.0], dim + [0.0])
+            m, keys, info = rw.apply_csg(mn, 256, ops, base["materials"], base["edgeKeys"], base["edgeInfo"])
+            w.apply_csg_operations(oracle_csg_ops(oracle_mod, ops), mn, 256)
+            o = w.generate_chunk_mesh(mn, 256)
+            assert np.array_equal(o["materials"], m)
+            # DESIGN.md deviation 4: the reference lists edges that start outside the Hermite grid; nothing reads them
+            idx = keys >> 2
+            ingrid = ((idx & 127) < 65) & (((idx >> 7) & 127) < 65) & (((idx >> 14) & 127) < 65)
+            ro, oo = np.argsort(keys[ingrid], kind="stable"), np.argsort(o["edgeKeys"], kind="stable")
+            assert np.array_equal(keys[ingrid][ro], o["edgeKeys"][oo])
+            assert beq(info[ingrid][ro], o["edgeInfo"][oo])
+            oc = rw.construct_octree(mn, 256, m, keys, info)
+            if oc is None:
+                assert o["numNodes"] == 0
+                continue
+            verts, tris = rw.generate_mesh(256, oc)
+            assert beq(verts, o["vertices"]) and beq(tris, o["indices"]) and beq(rw.gather_seam_nodes(oc), o["seams"])
+        finally:
+            w.close()
+
+
+def test_live_cuckoo_kernel_on_reference_fixtures(ref_mod, golden_keys):
+    """the reference's Cuckoo_InsertKeys / Cuckoo_Find kernels on its own octree key fixtures
+    (test_cuckoo.cpp:120-178): every key inserted, found, value = its index"""
+    for name in sorted(golden_keys)[:4]:
+        keys = np.unique(golden_keys[name].astype(np.uint32))
+        t = ref_mod.Cuckoo(len(keys))
+        t.insert_keys(keys)
+        for i in range(0, len(keys), max(1, len(keys) // 200)):
+            assert t.find(keys[i]) == i
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA path vs the golden vectors (GPU box: no /root/reference there)
+# ---------------------------------------------------------------------------------------------
+def _dump_stages(got):
+    q = got["nodeQEFs"].reshape(-1, 16).copy()
+    q[:, 6:8] = 0
+    return dict(edgeKeys=got["edgeKeys"], edgeInfo=got["edgeInfo"], codes=got["nodeCodes"], edgeMasks=got["nodeEdgeMasks"],
+                matWords=got["nodeMaterials"], qefs=q, positions=got["nodePositions"], normals=got["nodeNormals"])
+
+
+@pytest.mark.gpu
+def test_gpu_equals_reference_kernels_golden(lc, golden):
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        assert digest(lc.Compute_GetNoiseImage()) == str(golden["image_sha256"])
+        # origin chunk, full arrays
+        mn = [int(v) for v in golden["origin/min_size"][:3]]
+        got = ctx.debugDumpChunk(mn, 256)
+        assert np.array_equal(got["materials"], golden["origin/materials_u8"])
+        for k, v in _dump_stages(got).items():
+            assert beq(v, golden[f"origin/{k}"].view(np.float32).reshape(v.shape) if k == "qefs" else golden[f"origin/{k}"]), k
+        mesh, seams = lc.MeshBuffer(), []
+        assert ctx.generateChunkMesh(mn, 256, mesh, seams) == 0
+        assert beq(mesh.triangles["indices_"][:mesh.numTriangles], golden["origin/indices"])
+        gv = golden["origin/vertices"]
+        v = mesh.vertices[:mesh.numVertices]
+        for f in ("xyz", "normal", "colour"):
+            assert beq(v[f], gv[f]), f
+        gs = golden["origin/seams"]
+        for f in ("localspaceMin", "position", "normal"):
+            assert beq(seams[0][f], gs[f]), f
+        ctx.freeChunkOctree(mn, 256)
+        # digest cases
+        for name in golden["digest_cases"]:
+            name = str(name)
+            ms = [int(x) for x in golden[f"d/{name}/min_size"]]
+            want = dict(zip(STAGES, (str(s) for s in golden[f"d/{name}/sha256"])))
+            counts = [int(x) for x in golden[f"d/{name}/counts"]]
+            got = ctx.debugDumpChunk(ms[:3], ms[3])
+            assert [got["numEdges"], got["numNodes"], got["numTriangles"], got["numSeamNodes"]] == counts, name
+            assert digest(got["materials"].astype(np.int32)) == want["materials"], name
+            if counts[1] == 0:
+                continue
+            for k, v in _dump_stages(got).items():
+                assert digest(v) == want[k], f"{name}: stage {k}"
+            mesh, seams = lc.MeshBuffer(max_vertices=1 << 15, max_triangles=1 << 16), []
+            assert ctx.generateChunkMesh(ms[:3], ms[3], mesh, seams) == 0
+            assert digest(mesh.triangles["indices_"][:mesh.numTriangles]) == want["indices"], name
+            verts = np.zeros(mesh.numVertices, np.dtype([("xyz", np.float32, 4), ("normal", np.float32, 4), ("colour", np.float32, 4)]))
+            for f in ("xyz", "normal", "colour"):
+                verts[f] = mesh.vertices[:mesh.numVertices][f]
+            assert digest(verts) == want["vertices"], name
+            sn = np.zeros(len(seams[0]), np.dtype([("localspaceMin", np.int32, 4), ("position", np.float32, 4), ("normal", np.float32, 4)]))
+            for f in ("localspaceMin", "position", "normal"):
+                sn[f] = seams[0][f]
+            assert digest(sn) == want["seams"], name
+            ctx.freeChunkOctree(ms[:3], ms[3])
+    finally:
+        ctx.destroy()
+
+
+@pytest.mark.gpu
+def test_gpu_equals_reference_kernels_golden_csg(lc, golden):
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        mn = [int(v) for v in golden["origin/min_size"][:3]]
+        ops = [lc.CSGOperationInfo.make(int(o["type"]), int(o["brushShape"]), int(o["material"]), [float(x) for x in o["origin"][:3]],
+                                        [float(x) for x in o["dimensions"][:3]], float(o["rotateY"])) for o in golden["csg/ops"]]
+        assert ctx.applyCSGOperations(ops, mn, 256) == 0
+        got = ctx.debugDumpChunk(mn, 256)
+        assert np.array_equal(got["materials"], golden["csg/materials_u8"])
+        order = np.argsort(got["edgeKeys"], kind="stable")
+        assert np.array_equal(got["edgeKeys"][order], golden["csg/edgeKeys_sorted"])
+        assert beq(got["edgeInfo"][order], golden["csg/edgeInfo_sorted"])
+        assert beq(got["nodeCodes"], golden["csg/codes"]) and beq(got["nodeMaterials"], golden["csg/matWords"])
+        assert beq(got["nodePositions"], golden["csg/positions"]) and beq(got["nodeNormals"], golden["csg/normals"])
+        mesh, seams = lc.MeshBuffer(), []
+        assert ctx.generateChunkMesh(mn, 256, mesh, seams) == 0
+        assert beq(mesh.triangles["indices_"][:mesh.numTriangles], golden["csg/indices"])
+        gs = golden["csg/seams"]
+        for f in ("localspaceMin", "position", "normal"):
+            assert beq(seams[0][f], gs[f]), f
+    finally:
+        ctx.destroy()
