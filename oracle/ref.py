@@ -75,6 +75,11 @@ def lib():
     return _lib
 
 
+def set_num_threads(n):
+    """OpenMP threads over the work-items of each NDRange (torchrun exports OMP_NUM_THREADS=1)"""
+    return int(lib().ref_set_num_threads(int(n)))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

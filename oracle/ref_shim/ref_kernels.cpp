@@ -16,6 +16,9 @@
 // tables with atomics (Cuckoo_InsertKeys) run serially, in work-item order.
 #include <cfloat>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "clc.hpp"
 
@@ -126,6 +129,16 @@ static_assert(sizeof(csg_prog::CSGOperation) == 48, "CSGOperation (apply_csg_ope
 extern "C" {
 
 int ref_voxels_per_chunk(void) { return VOXELS_PER_CHUNK; }
+// threads used for the work-items of every NDRange (a CPU OpenCL runtime would use all cores)
+int ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 // one DensityFunc evaluation (noise.cl:225-268), for spot checks
 float ref_DensityFunc(const unsigned char *rgba, float x, float y, float z)
