@@ -437,8 +437,11 @@ struct lvn_meshgen {
     int numStreams = 1;                // of the last batch
     cudaStream_t laneStreams[LVN_MAX_STREAMS] = {nullptr};   // [0] unused: the context's stream
     cudaStream_t copyStream = nullptr;
-    cudaEvent_t evFork = nullptr, evCopy = nullptr;
+    cudaStream_t pubStream = nullptr;      // k_publish of the host path (kernels_chunk.cu)
+    cudaEvent_t evFork = nullptr, evCopy = nullptr, evPubJoin = nullptr;
     cudaEvent_t evLane[LVN_MAX_LANES] = {nullptr};
+    cudaEvent_t evPub[LVN_MAX_LANES] = {nullptr};
+    cudaEvent_t evRows[LVN_MAX_LANES] = {nullptr};
     cudaEvent_t evJoin[LVN_MAX_STREAMS] = {nullptr};
     int numLanes = 0;
     int laneFirst[LVN_MAX_LANES + 1] = {0};      // lane k owns internal chunks [laneFirst[k], laneFirst[k+1])
@@ -477,6 +480,14 @@ extern "C" lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk)
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
     for (int i = 1; i < LVN_MAX_STREAMS; i++) cudaStreamCreateWithFlags(&ctx->laneStreams[i], cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    {   // k_publish must slip in between the blocks of a running Hermite kernel: highest priority
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&ctx->pubStream, cudaStreamNonBlocking, hi);
+    }
+    cudaEventCreateWithFlags(&ctx->evPubJoin, cudaEventDisableTiming);
+    for (int i = 0; i < LVN_MAX_LANES; i++) cudaEventCreateWithFlags(&ctx->evPub[i], cudaEventDisableTiming);
+    for (int i = 0; i < LVN_MAX_LANES; i++) cudaEventCreateWithFlags(&ctx->evRows[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming);
     for (int i = 0; i < LVN_MAX_LANES; i++) cudaEventCreateWithFlags(&ctx->evLane[i], cudaEventDisableTiming);
@@ -509,6 +520,10 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 1; i < LVN_MAX_STREAMS; i++) if (ctx->laneStreams[i]) cudaStreamDestroy(ctx->laneStreams[i]);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->pubStream) cudaStreamDestroy(ctx->pubStream);
+    if (ctx->evPubJoin) cudaEventDestroy(ctx->evPubJoin);
+    for (int i = 0; i < LVN_MAX_LANES; i++) if (ctx->evPub[i]) cudaEventDestroy(ctx->evPub[i]);
+    for (int i = 0; i < LVN_MAX_LANES; i++) if (ctx->evRows[i]) cudaEventDestroy(ctx->evRows[i]);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
     for (int i = 0; i < LVN_MAX_LANES; i++) if (ctx->evLane[i]) cudaEventDestroy(ctx->evLane[i]);
@@ -698,6 +713,8 @@ static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies)
     if (copies) {
         CU(cudaEventRecord(ctx->evCopy, ctx->copyStream));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->evCopy, 0));
+        CU(cudaEventRecord(ctx->evPubJoin, ctx->pubStream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evPubJoin, 0));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return LVN_SUCCESS;
@@ -882,7 +899,6 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             cudaStream_t ls = (k % R) == 0 ? st : ctx->laneStreams[k % R];
             const int first = ctx->laneFirst[k], cnt = ctx->laneFirst[k + 1] - first;
             ChunkHdr *hdrs = ctx->d_hdrs.p + k;
-            ChunkHdr *hostHdrs = h_hdrs_dev + k;
             LVN_TRACE_EV(0);
             LaneArenas lane;
             lane.caps = caps;
@@ -895,8 +911,19 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             ctx->laneBase[k] = lane.base;
             {
                 StageTimer t(ctx, LVN_STAGE_CLASSIFY, 1);
-                launch_rows(d, ctx->d_descs.p, first, cnt, ctx->d_heights.p, ctx->d_colMin.p, ctx->d_colMax.p, hdrs, hostHdrs,
+                launch_rows(d, ctx->d_descs.p, first, cnt, ctx->d_heights.p, ctx->d_colMin.p, ctx->d_colMax.p, hdrs, nullptr,
                             ws, lane, ls);
+            }
+            // The lane's headers and counters are final once k_rows has run.  On the host path they
+            // are published right away from a side stream, so that the host can size and queue the
+            // lane's copies (behind evLane) long before the lane's last kernel ends: the copy engine
+            // then starts the moment the lane is done, with no host round trip in between.
+            const bool earlyPublish = out && S > 1;
+            if (earlyPublish) {
+                CU(cudaEventRecord(ctx->evRows[k], ls));
+                CU(cudaStreamWaitEvent(ctx->pubStream, ctx->evRows[k], 0));
+                launch_publish(ctx->d_hdrs.p + first + k, h_hdrs_dev + first + k, cnt + 1, ctx->pubStream);
+                CU(cudaEventRecord(ctx->evPub[k], ctx->pubStream));
             }
             LVN_TRACE_EV(1);
             {
@@ -912,12 +939,13 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                     dbg.codes = ctx->d_dbgCodes.p; dbg.edgeMasks = ctx->d_dbgMasks.p; dbg.matWords = ctx->d_dbgMats.p;
                     dbg.qefs = ctx->d_dbgQefs.p; dbg.positions = ctx->d_dbgPos.p; dbg.normals = ctx->d_dbgNrm.p;
                 }
-                launch_leaves(dp, d, ctx->d_descs.p, hdrs, ws, lane, (ArenaCounters *)(h_hdrs_dev + first + cnt + k),
+                launch_leaves(dp, d, ctx->d_descs.p, hdrs, ws, lane, nullptr,
                               ctx->d_edgeInfo.p, ctx->d_vertices.p, ctx->d_tris.p, ctx->d_seams.p, dbg, ls);
             }
             LVN_TRACE_EV(3);
+            if (earlyPublish) CU(cudaEventRecord(ctx->evLane[k], ls));
+            else launch_publish(ctx->d_hdrs.p + first + k, h_hdrs_dev + first + k, cnt + 1, ls);
             LVN_TRACE_EV(4);
-            if (S > 1) CU(cudaEventRecord(ctx->evLane[k], ls));
             return LVN_SUCCESS;
         };
 
@@ -932,7 +960,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             for (int k = 0; k < S; k++) {
                 while (issued < S && issued < k + 2) LV(enqueue_lane(issued++));
                 if (overflow || hostFull) continue;   // keep issuing: the retry needs every lane's counts
-                if (S > 1) CU(cudaEventSynchronize(ctx->evLane[k]));
+                if (S > 1) CU(cudaEventSynchronize(ctx->evPub[k]));
                 else CU(cudaStreamSynchronize(st));
                 const ArenaCounters c = *lane_counters_host(k);
                 if (c.overflow) { overflow = true; continue; }
@@ -943,6 +971,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 // the lane's three arenas in one batched copy: 12 separate memcpys of a 4-lane batch
                 // cost ~55 us more than the same bytes in one (profiles/micro/copy_granularity.cu)
                 cudaStream_t cs = S > 1 ? ctx->copyStream : st;
+                if (S > 1) CU(cudaStreamWaitEvent(cs, ctx->evLane[k], 0));   // the lane's last kernel
                 void *dst[3], *src[3];
                 size_t len[3];
                 size_t m = 0;
