@@ -440,9 +440,11 @@ def main():
                           "C restatement of the reference pipeline (oracle/lvn_oracle.c)"}
         from oracle import ref as R
         if R.available():
-            # the reference's own kernels on the host cores: ~20 s of CPU work on a spread sample
-            sample = reference_sample(ms, 24)
-            value, rdt, rthreads, non_empty = time_reference_kernels(lc.Compute_GetNoiseImage(), sample, 1, 1)
+            # the reference's own kernels on the host cores: a spread sample sized for ~12 s of CPU work
+            image = lc.Compute_GetNoiseImage()
+            rate, _, _, _ = time_reference_kernels(image, reference_sample(ms, 16), 1, 1)
+            sample = reference_sample(ms, max(16, min(nchunks, int(12.0 * rate))))
+            value, rdt, rthreads, non_empty = time_reference_kernels(image, sample, 1, 0)
             line["cpu_baseline"] = {"value": value, "unit": "chunks/s", "cores": int(rthreads), "kind": "reference",
                                     "sample": f"{len(sample)} of the workload's {nchunks} chunks once ({rdt:.1f} s; evenly spread, "
                                               f"{non_empty} contain surface), leven/cl kernels compiled for the host (oracle/_ref), "

@@ -206,17 +206,29 @@ __device__ __forceinline__ float2 corner2x2(const float2 gA, const float2 gB, fl
 
 __device__ __forceinline__ float2 snoise2x2(const float2 *__restrict__ grad, float2 px, float2 py, float2 nz)
 {
+#ifndef LVN_X2_XU_FLOOR
     const float2 M = rep2(12582912.f);   // 1.5 * 2^23
     const float2 s = mul2(add2(px, py), rep2(LVN_F2), nz);
     const float2 mx = __fadd2_rd(add2(px, s), M), my = __fadd2_rd(add2(py, s), M);
     const float2 ix = sub2(mx, M), iy = sub2(my, M);
+    const int iiA = __float_as_int(mx.x), jjA = __float_as_int(my.x), iiB = __float_as_int(mx.y), jjB = __float_as_int(my.y);
+#else   // floor and float->int on the XU pipe instead of four packed adds on the FMA pipe
+    const float2 s = mul2(add2(px, py), rep2(LVN_F2), nz);
+    const float2 vx = add2(px, s), vy = add2(py, s);
+    const float2 ix = make_float2(floorf(vx.x), floorf(vx.y)), iy = make_float2(floorf(vy.x), floorf(vy.y));
+    const int iiA = __float2int_rz(ix.x), jjA = __float2int_rz(iy.x), iiB = __float2int_rz(ix.y), jjB = __float2int_rz(iy.y);
+#endif
     const float2 t = mul2(add2(ix, iy), rep2(LVN_G2), nz);
     const float2 x0 = sub2(px, sub2(ix, t)), y0 = sub2(py, sub2(iy, t));
     const bool xyA = x0.x > y0.x, xyB = x0.y > y0.y;
     const float2 o1x = make_float2(xyA ? 1.f : 0.f, xyB ? 1.f : 0.f);
+#ifndef LVN_X2_XU_FLOOR
     const float2 o1y = sub2(rep2(1.f), o1x);
-    const float2 *gA = grad + ((__float_as_int(my.x) & 255) * LVN_G2PITCH + (__float_as_int(mx.x) & 255));
-    const float2 *gB = grad + ((__float_as_int(my.y) & 255) * LVN_G2PITCH + (__float_as_int(mx.y) & 255));
+#else
+    const float2 o1y = make_float2(xyA ? 0.f : 1.f, xyB ? 0.f : 1.f);
+#endif
+    const float2 *gA = grad + ((jjA & 255) * LVN_G2PITCH + (iiA & 255));
+    const float2 *gB = grad + ((jjB & 255) * LVN_G2PITCH + (iiB & 255));
     const float2 g0A = __ldg(gA), g1A = __ldg(gA + (xyA ? 1 : LVN_G2PITCH)), g2A = __ldg(gA + (LVN_G2PITCH + 1));
     const float2 g0B = __ldg(gB), g1B = __ldg(gB + (xyB ? 1 : LVN_G2PITCH)), g2B = __ldg(gB + (LVN_G2PITCH + 1));
 
@@ -226,14 +238,48 @@ __device__ __forceinline__ float2 snoise2x2(const float2 *__restrict__ grad, flo
     return mul2(rep2(70.f), add2(add2(n0, n1), n2), nz);
 }
 
+// Per-octave constants of the fractals, folded in IEEE binary32 exactly like the unrolled scalar
+// code folds them: amplitude_i = amplitude_(i-1) * persistence, frequency_i = frequency_(i-1) *
+// lacunarity, exponent_i = 1 / frequency_i.
+template <int N> struct OctaveTable { float v[N]; };
+template <int N> __host__ __device__ constexpr OctaveTable<N> amplitude_table(float persistence)
+{
+    OctaveTable<N> t = {};
+    float a = 1.f;
+    for (int i = 0; i < N; i++) { t.v[i] = a; a *= persistence; }
+    return t;
+}
+template <int N> __host__ __device__ constexpr OctaveTable<N> exponent_table(float lacunarity)
+{
+    OctaveTable<N> t = {};
+    float f = 1.f;
+    for (int i = 0; i < N; i++) { t.v[i] = 1.f / f; f *= lacunarity; }
+    return t;
+}
+
+// Terrain's three fractals (noise.cl:207-222)
+static __constant__ OctaveTable<7> c_x2_ridgedExp = exponent_table<7>(2.114352f);
+static __constant__ OctaveTable<4> c_x2_billowAmp = amplitude_table<4>(0.433f);
+static __constant__ OctaveTable<2> c_x2_b2Amp = amplitude_table<2>(0.15f);
+
+// Measured on B200 (512-chunk ring, Hermite kernel): octave loops unrolled 187 us (64 registers) /
+// 195 us (48); rolled with the tables above (4 snoise2 bodies instead of 14, 40 registers) 190 us;
+// the evaluation out of line (__noinline__) 188 us; floor() and float->int on the XU pipe instead
+// of the packed adds (LVN_X2_XU_FLOOR) 190 us.  All within 4 %: the kernel is bound by the FMA
+// pipe while it evaluates noise, not by instruction fetch or occupancy.
+#ifndef LVN_X2_UNROLL
+#define LVN_X2_UNROLL 1
+#endif
+
 template <int OCTAVES>
 __device__ __forceinline__ float2 basic_fractal_x2(const float2 *__restrict__ grad, float frequency, float lacunarity,
-                                                   float persistence, float2 px, float2 py, float2 nz)
+                                                   float persistence, const float *amp, float2 px, float2 py, float2 nz)
 {
     float2 noise = rep2(0.f);
-    float amplitude = 1.f;
     px = mul2(px, rep2(frequency), nz);
     py = mul2(py, rep2(frequency), nz);
+#if LVN_X2_UNROLL
+    float amplitude = 1.f;
 #pragma unroll
     for (int i = 0; i < OCTAVES; i++) {
         noise = add2(noise, mul2(snoise2x2(grad, px, py, nz), rep2(amplitude), nz));
@@ -241,19 +287,31 @@ __device__ __forceinline__ float2 basic_fractal_x2(const float2 *__restrict__ gr
         py = mul2(py, rep2(lacunarity), nz);
         amplitude *= persistence;
     }
+#else
+#pragma unroll 1
+    for (int i = 0; i < OCTAVES; i++) {
+        noise = add2(noise, mul2(snoise2x2(grad, px, py, nz), rep2(amp[i]), nz));
+        px = mul2(px, rep2(lacunarity), nz);
+        py = mul2(py, rep2(lacunarity), nz);
+    }
+#endif
     return noise;
 }
 
 template <int OCTAVES>
 __device__ __forceinline__ float2 ridged_multifractal_x2(const float2 *__restrict__ grad, float lacunarity, float gain,
-                                                         float offset, float2 px, float2 py, float2 nz)
+                                                         float offset, const float *expo, float2 px, float2 py, float2 nz)
 {
     float2 signal = snoise2x2(grad, px, py, nz);
     signal = sub2(rep2(offset), make_float2(fabsf(signal.x), fabsf(signal.y)));
     signal = mul2(signal, signal, nz);
     float2 noise = signal;
+#if LVN_X2_UNROLL
     float frequency = 1.f;
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int i = 0; i < OCTAVES; i++) {
         px = mul2(px, rep2(lacunarity), nz);
         py = mul2(py, rep2(lacunarity), nz);
@@ -261,21 +319,29 @@ __device__ __forceinline__ float2 ridged_multifractal_x2(const float2 *__restric
         signal = snoise2x2(grad, px, py, nz);
         signal = sub2(rep2(offset), make_float2(fabsf(signal.x), fabsf(signal.y)));
         signal = mul2(signal, weight, nz);
+#if LVN_X2_UNROLL
         const float exponent = 1.f / frequency;   // pow(frequency, -1.f)
         frequency *= lacunarity;
+#else
+        const float exponent = expo[i];
+#endif
         noise = add2(noise, mul2(signal, rep2(exponent), nz));
     }
     return mul2(noise, rep2(1.f / (float)OCTAVES), nz);
 }
 
 // terrain_height() at (xA, zA) and (xB, zB): x = (xA, xB), z = (zA, zB); negZero must be -0.f
+#ifdef LVN_X2_NOINLINE
+__device__ __noinline__ float2 terrain_height_x2(const float2 *__restrict__ grad, float negZero, float2 x, float2 z)
+#else
 __device__ __forceinline__ float2 terrain_height_x2(const float2 *__restrict__ grad, float negZero, float2 x, float2 z)
+#endif
 {
     const float2 nz = rep2(negZero);
     const float2 px = mul2(x, rep2(1.f / 2000.f), nz), py = mul2(z, rep2(1.f / 2000.f), nz);
-    const float2 r = ridged_multifractal_x2<7>(grad, 2.114352f, 1.5241f, 1.f, px, py, nz);
-    const float2 bi = basic_fractal_x2<4>(grad, 0.24f, 1.8754f, 0.433f, mul2(px, rep2(-4.33f), nz), mul2(py, rep2(7.98f), nz), nz);
-    const float2 b2 = basic_fractal_x2<2>(grad, 0.63f, 2.2f, 0.15f, px, py, nz);
+    const float2 r = ridged_multifractal_x2<7>(grad, 2.114352f, 1.5241f, 1.f, c_x2_ridgedExp.v, px, py, nz);
+    const float2 bi = basic_fractal_x2<4>(grad, 0.24f, 1.8754f, 0.433f, c_x2_billowAmp.v, mul2(px, rep2(-4.33f), nz), mul2(py, rep2(7.98f), nz), nz);
+    const float2 b2 = basic_fractal_x2<2>(grad, 0.63f, 2.2f, 0.15f, c_x2_b2Amp.v, px, py, nz);
     float h[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {   // the tail of Terrain, scalar per position exactly as terrain()

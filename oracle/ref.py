@@ -37,31 +37,37 @@ QEF_DTYPE = np.dtype([("ATA", np.float32, 6), ("pad", np.float32, 2), ("ATb", np
 CSG_DTYPE = np.dtype([("type", np.int32), ("brushShape", np.int32), ("material", np.int32), ("rotateY", np.float32),
                       ("origin", np.float32, 4), ("dimensions", np.float32, 4)])
 
-_lib = None
+_libs = {}
 
 
-def available():
-    return os.path.exists(LIB_PATH)
+def _lib_path(V):
+    return LIB_PATH if V == 64 else os.path.join(_HERE, "_ref", f"libleven_cl_ref_v{V}.so")
+
+
+def available(V=64):
+    return os.path.exists(_lib_path(V))
 
 
 def build(force=False):
     """compile the reference kernels where they lie; a no-op (returns False) when /root/reference is absent"""
     if not os.path.isdir(REFERENCE_CL):
         return available()
-    deps = [os.path.join(_HERE, "ref_shim", f) for f in ("ref_kernels.cpp", "clc.hpp", "translate.py")]
-    if force or not available() or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+    deps = [os.path.join(_HERE, "ref_shim", f) for f in ("ref_kernels.cpp", "clc.hpp", "translate.py")] + [os.path.join(_HERE, "Makefile")]
+    libs = [_lib_path(V) for V in (64, 32, 16)]
+    stale = any(not os.path.exists(l) for l in libs) or any(os.path.getmtime(d) > min(os.path.getmtime(l) for l in libs) for d in deps)
+    if force or stale:
         env = dict(os.environ)
         env.pop("CC", None); env.pop("CXX", None)
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "ref"], env=env)
     return True
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not available():
-            raise ImportError(f"{LIB_PATH} is missing: `make -C oracle ref` (needs /root/reference)")
-        L = C.CDLL(LIB_PATH)
+def lib(V=64):
+    """the reference programs built for voxelsPerChunk = V (64, 32 or 16)"""
+    if V not in _libs:
+        if not available(V):
+            raise ImportError(f"{_lib_path(V)} is missing: `make -C oracle ref` (needs /root/reference)")
+        L = C.CDLL(_lib_path(V))
         L.ref_DensityFunc.restype = C.c_float
         L.ref_DensityFunc.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
         L.ref_snoise2.restype = C.c_float
@@ -70,9 +76,9 @@ def lib():
         L.ref_snoise3.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
         L.ref_Cuckoo_Find.restype = C.c_uint32
         L.ref_Cuckoo_Hash.restype = C.c_uint32
-        assert L.ref_voxels_per_chunk() == 64
-        _lib = L
-    return _lib
+        assert L.ref_voxels_per_chunk() == V
+        _libs[V] = L
+    return _libs[V]
 
 
 def set_num_threads(n):
@@ -166,11 +172,13 @@ class Cuckoo:
 
 
 class RefWorld:
-    """The reference pipeline for one chunk, kernels from the reference text, V = 64."""
-    V, H, F = 64, 65, 66
+    """The reference pipeline for one chunk, kernels from the reference text."""
 
-    def __init__(self, image, default_material=0):
-        self.L = lib()
+    def __init__(self, image, default_material=0, voxels_per_chunk=64):
+        self.V = int(voxels_per_chunk)
+        self.H, self.F = self.V + 1, self.V + 2
+        self.shift = self.V.bit_length()          # VOXEL_INDEX_SHIFT = log2(V) + 1
+        self.L = lib(self.V)
         self.image = np.ascontiguousarray(image, np.uint8)
         assert self.image.size == 256 * 256 * 4
         self.default_material = int(default_material)

@@ -291,3 +291,125 @@ def test_gpu_equals_reference_kernels_golden_csg(lc, golden):
             assert beq(seams[0][f], gs[f]), f
     finally:
         ctx.destroy()
+
+
+# ---------------------------------------------------------------------------------------------
+# smaller contexts (the reference builds its programs per voxelsPerChunk, compute.cpp:256-278)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V", [32, 16])
+def test_live_smaller_chunk_sizes(oracle_mod, ref_mod, V):
+    if not ref_mod.available(V):
+        pytest.skip(f"reference programs for V={V} not built")
+    image = oracle_mod.noise_image(SEED)
+    rw = ref_mod.RefWorld(image, voxels_per_chunk=V)
+    w = oracle_mod.World(image=image, default_material=0, voxels_per_chunk=V)
+    try:
+        size0 = V * 4
+        done = 0
+        for cx, cz, scale in ((0, 0, 1), (3, -2, 1), (-5, 7, 1), (1, 1, 2), (-2, 0, 4)):
+            size = size0 * scale
+            h = -rw.density(np.float32((cx + 0.5) * size / 4), np.float32(0.0), np.float32((cz + 0.5) * size / 4))
+            mn = [cx * size, int(h * 4 // size) * size, cz * size]
+            r = rw.generate_chunk_mesh(mn, size)
+            o = w.generate_chunk_mesh(mn, size)
+            w.free_chunk_octree(mn, size)
+            for k in COUNTS:
+                assert o[k] == r[k], (V, mn, size, k)
+            if r["numNodes"] == 0:
+                continue
+            for k in STAGES:
+                a, b = (zero_pad(o[k]), zero_pad(r[k])) if k == "qefs" else (o[k], r[k])
+                assert beq(a, b), (V, mn, size, k)
+            done += 1
+        assert done >= 3
+    finally:
+        w.close()
+
+
+@pytest.mark.gpu
+def test_gpu_equals_live_reference_kernels(lc, ref_mod):
+    """the CUDA path against the reference kernels run on the spot (the library ships with the
+    snapshot): random chunks of the default world, LOD0 / LOD1, every stage and the exported mesh"""
+    image = lc.Compute_GetNoiseImage()
+    rw = ref_mod.RefWorld(image)
+    ctx = lc.Compute_MeshGenContext.create(64)
+    rng = np.random.default_rng(4242)
+    try:
+        done = 0
+        for _ in range(30):
+            cx, cz = (int(v) for v in rng.integers(-8, 8, 2))
+            size = int(rng.choice([256, 256, 256, 512]))
+            h = -rw.density(np.float32(cx * 64.0 + 32), np.float32(0.0), np.float32(cz * 64.0 + 32))
+            mn = [cx * 256 // size * size, int(h * 4 // size) * size, cz * 256 // size * size]
+            r = rw.generate_chunk_mesh(mn, size)
+            got = ctx.debugDumpChunk(mn, size)
+            assert [got["numEdges"], got["numNodes"], got["numTriangles"], got["numSeamNodes"]] == [r[k] for k in COUNTS], (mn, size)
+            assert np.array_equal(got["materials"].astype(np.int32), r["materials"])
+            if r["numNodes"] == 0:
+                continue
+            st = _dump_stages(got)
+            q = r["qefs"].copy(); q["pad"] = 0
+            want = dict(edgeKeys=r["edgeKeys"], edgeInfo=r["edgeInfo"], codes=r["codes"], edgeMasks=r["edgeMasks"], matWords=r["matWords"],
+                        qefs=q.view(np.float32).reshape(-1, 16), positions=r["positions"], normals=r["normals"])
+            for k, v in st.items():
+                assert beq(v, want[k]), (mn, size, k)
+            mesh, seams = lc.MeshBuffer(max_vertices=1 << 15, max_triangles=1 << 16), []
+            assert ctx.generateChunkMesh(mn, size, mesh, seams) == 0
+            assert beq(mesh.triangles["indices_"][:mesh.numTriangles], r["indices"])
+            for f in ("xyz", "normal", "colour"):
+                assert beq(mesh.vertices[:mesh.numVertices][f], r["vertices"][f]), f
+            for f in ("localspaceMin", "position", "normal"):
+                assert beq(seams[0][f], r["seams"][f]), f
+            ctx.freeChunkOctree(mn, size)
+            done += 1
+            if done >= 8:
+                break
+        assert done >= 5
+    finally:
+        ctx.destroy()
+
+
+@pytest.mark.gpu
+def test_gpu_csg_equals_live_reference_kernels(lc, ref_mod, surface_cy):
+    """random CSG scripts: apply_csg_operation.cl run on the spot vs the CUDA CSG path"""
+    image = lc.Compute_GetNoiseImage()
+    rw = ref_mod.RefWorld(image)
+    rng = np.random.default_rng(777)
+    mn = [-512, surface_cy * 256, 256]
+    base = rw.generate_chunk_mesh(mn, 256)
+    for trial in range(4):
+        ctx = lc.Compute_MeshGenContext.create(64)
+        try:
+            n = int(rng.integers(1, 6))
+            ops = np.zeros(n, ref_mod.CSG_DTYPE)
+            for i in range(n):
+                add = bool(rng.integers(0, 2))
+                org = [mn[0] / 4 + float(rng.integers(-2, 67)) + 0.5, surface_cy * 64 + float(rng.integers(0, 64)) + 0.5,
+                       mn[2] / 4 + float(rng.integers(-2, 67)) + 0.5]
+                dim = [float(rng.integers(1, 14)) for _ in range(3)]
+                ops[i] = (0 if add else 1, int(rng.integers(0, 2)), int(rng.integers(1, 5)) if add else 201,
+                          float(rng.uniform(-1.5, 1.5)) if trial % 2 else 0.0, org + [0.0], dim + [0.0])
+            m, keys, info = rw.apply_csg(mn, 256, ops, base["materials"], base["edgeKeys"], base["edgeInfo"])
+            lops = [lc.CSGOperationInfo.make(int(o["type"]), int(o["brushShape"]), int(o["material"]), [float(x) for x in o["origin"][:3]],
+                                             [float(x) for x in o["dimensions"][:3]], float(o["rotateY"])) for o in ops]
+            assert ctx.applyCSGOperations(lops, mn, 256) == 0
+            got = ctx.debugDumpChunk(mn, 256)
+            assert np.array_equal(got["materials"].astype(np.int32), m)
+            idx = keys >> 2
+            ingrid = ((idx & 127) < 65) & (((idx >> 7) & 127) < 65) & (((idx >> 14) & 127) < 65)   # DESIGN.md deviation 4
+            ro, go = np.argsort(keys[ingrid], kind="stable"), np.argsort(got["edgeKeys"], kind="stable")
+            assert np.array_equal(keys[ingrid][ro], got["edgeKeys"][go])
+            assert beq(info[ingrid][ro], got["edgeInfo"][go])
+            oc = rw.construct_octree(mn, 256, m, keys, info)
+            if oc is None:
+                assert got["numNodes"] == 0
+                continue
+            assert beq(got["nodeCodes"], oc["codes"]) and beq(got["nodePositions"], oc["positions"]) and beq(got["nodeNormals"], oc["normals"])
+            verts, tris = rw.generate_mesh(256, oc)
+            mesh, seams = lc.MeshBuffer(max_vertices=1 << 15, max_triangles=1 << 16), []
+            assert ctx.generateChunkMesh(mn, 256, mesh, seams) == 0
+            assert beq(mesh.triangles["indices_"][:mesh.numTriangles], tris)
+            for f in ("xyz", "normal", "colour"):
+                assert beq(mesh.vertices[:mesh.numVertices][f], verts[f]), f
+        finally:
+            ctx.destroy()
