@@ -924,6 +924,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 CU(cudaStreamWaitEvent(ctx->pubStream, ctx->evRows[k], 0));
                 launch_publish(ctx->d_hdrs.p + first + k, h_hdrs_dev + first + k, cnt + 1, ctx->pubStream);
                 CU(cudaEventRecord(ctx->evPub[k], ctx->pubStream));
+                ctx->stats.launches[LVN_STAGE_CLASSIFY] += 1;   // k_publish
             }
             LVN_TRACE_EV(1);
             {
@@ -944,7 +945,10 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             }
             LVN_TRACE_EV(3);
             if (earlyPublish) CU(cudaEventRecord(ctx->evLane[k], ls));
-            else launch_publish(ctx->d_hdrs.p + first + k, h_hdrs_dev + first + k, cnt + 1, ls);
+            else {
+                launch_publish(ctx->d_hdrs.p + first + k, h_hdrs_dev + first + k, cnt + 1, ls);
+                ctx->stats.launches[LVN_STAGE_CLASSIFY] += 1;
+            }
             LVN_TRACE_EV(4);
             return LVN_SUCCESS;
         };

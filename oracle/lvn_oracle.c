@@ -16,13 +16,14 @@
 #ifdef _OPENMP
 #include <omp.h>
 
+#endif
+
 /* dot(float4, float4): ONE built-in, one definition -- the same fma chain the simplex
  * dot products use, for every call site (qef.cl:25-27,149,182). */
 static inline float dot4(float ax, float ay, float az, float aw, float bx, float by, float bz, float bw)
 {
     return fmaf(aw, bw, fmaf(az, bz, fmaf(ay, by, ax * bx)));
 }
-#endif
 
 #if defined(__x86_64__) && defined(__GNUC__)
 /* fast fmaf on FMA-capable hosts, libm fmaf elsewhere: same result */
