@@ -215,6 +215,48 @@ void lvn_free_pinned(void *p);
 int lvn_measure_fp32_peak(double *tflops);
 int lvn_meshgen_get_stats(lvn_meshgen *ctx, lvn_stage_stats *out, int reset);
 
+/* ---- seam meshes between clipmap nodes (the consumer of SeamNodeInfo) ------- */
+
+/* One active clipmap node whose seam nodes may feed a host node's seam: what
+ * GenerateClipmapSeamMesh (clipmap.cpp:573-611) hands to SelectSeamNodes (clipmap.cpp:542-569). */
+typedef struct lvn_seam_neighbour {
+    int32_t index;        /* 0..7: the slot of the host's 2x2x2 neighbourhood the node lies in
+                             (CHILD_MIN_OFFSETS, volume_constants.h:24-35; 0 = the host node itself) */
+    int32_t min[3];       /* the node's min, world units */
+    int32_t size;         /* the node's size, world units (any LOD) */
+    int32_t firstNode;    /* its SeamNodeInfo records, as generateChunkMesh returned them: */
+    int32_t numNodes;     /* seamNodes[firstNode .. firstNode + numNodes) */
+    int32_t pad;
+} lvn_seam_neighbour;
+
+typedef struct lvn_seam_job {
+    int32_t hostMin[3];   /* ClipmapNode::min_ of the node that owns the seam */
+    int32_t hostSize;     /* ClipmapNode::size_ */
+    int32_t firstNeighbour, numNeighbours;   /* neighbours[firstNeighbour .. + numNeighbours) */
+    float   colour[3];    /* vertex colour (GenerateClipmapSeamMesh's colour argument) */
+    int32_t pad;
+} lvn_seam_job;
+
+typedef struct lvn_seam_result {
+    int32_t numVertices, numTriangles;       /* 0 / 0 when the seam has no triangle (octree.cpp:536-540) */
+    int32_t vertexOffset, triangleOffset;    /* into the caller's arenas; indices are seam-local */
+    int32_t numSelectedNodes;                /* nodes that passed SelectSeamNodes */
+    int32_t status;                          /* 0 or LVN_ERR_CAPACITY */
+} lvn_seam_result;
+
+/* GenerateClipmapSeamMesh for many host nodes in one launch: SelectSeamNodes +
+ * Octree_ConstructUpwards(hostMin, 2 * hostSize) + Octree_GenerateMesh (octree.cpp:23-148,196-549)
+ * as one thread block per seam.  Vertices come out in the reference's order (the DFS order of the
+ * seam octree); triangles are the same index triples with the same winding, ordered by (owner
+ * vertex, edge) instead of by the reference's recursion.  Host pointers in and out. */
+int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, const lvn_seam_job *jobs,
+                                 const lvn_seam_neighbour *neighbours, int numNeighbours,
+                                 const lvn_seam_node_info *seamNodes, int numSeamNodes,
+                                 lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                 lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                 lvn_seam_result *results);
+const char *lvn_seam_last_error(void);
+
 /* ---- utilities of the path (a9, a15), usable on their own ---------------- */
 
 /* FindNextPrime, primes.h (primes.cpp:32-59) */

@@ -129,6 +129,8 @@ ABI = {
     "lvn_cuckoo_prime": (_I, [_P]),
     "lvn_cuckoo_retries": (_I, [_P]),
     "lvn_cuckoo_destroy": (None, [_P]),
+    "lvn_seam_mesh_generate_batch": (_I, [_I, _I, _P, _P, _I, _P, _I, _P, _I64, _P, _I64, _P]),
+    "lvn_seam_last_error": (C.c_char_p, []),
 }
 
 _lib = None
@@ -478,3 +480,62 @@ class CuckooData:
         if self.h:
             lib().lvn_cuckoo_destroy(self.h)
             self.h = None
+
+
+# ---------------------------------------------------------------------------------------------
+# seam meshes between clipmap nodes (GenerateClipmapSeamMesh, clipmap.cpp:573-611)
+# ---------------------------------------------------------------------------------------------
+SeamNeighbour = np.dtype([("index", np.int32), ("min", np.int32, 3), ("size", np.int32), ("firstNode", np.int32),
+                          ("numNodes", np.int32), ("pad", np.int32)])
+SeamJob = np.dtype([("hostMin", np.int32, 3), ("hostSize", np.int32), ("firstNeighbour", np.int32), ("numNeighbours", np.int32),
+                    ("colour", np.float32, 3), ("pad", np.int32)])
+SeamResult = np.dtype([("numVertices", np.int32), ("numTriangles", np.int32), ("vertexOffset", np.int32),
+                       ("triangleOffset", np.int32), ("numSelectedNodes", np.int32), ("status", np.int32)])
+
+
+def PackSeamJobs(seams, colour=(1.0, 1.0, 1.0)):
+    """seams: [(hostMin, hostSize, [(neighbourIndex, neighbourMin, neighbourSize, SeamNodeInfo array), ...]), ...]
+    -> the three flat arrays of lvn_seam_mesh_generate_batch (jobs, neighbours, seam nodes)"""
+    jobs = np.zeros(len(seams), SeamJob)
+    nbs, nodes = [], []
+    first_node = 0
+    placed = {}     # a node's SeamNodeInfo array is uploaded once, however many seams it feeds
+    for s, (host_min, host_size, neighbours) in enumerate(seams):
+        jobs[s]["hostMin"] = host_min
+        jobs[s]["hostSize"] = host_size
+        jobs[s]["firstNeighbour"] = len(nbs)
+        jobs[s]["numNeighbours"] = len(neighbours)
+        jobs[s]["colour"] = colour
+        for index, nb_min, nb_size, arr in neighbours:
+            k = (tuple(nb_min), nb_size, id(arr))
+            if k not in placed:
+                a = np.ascontiguousarray(arr, SeamNodeInfo)
+                placed[k] = (first_node, len(a))
+                nodes.append(a)
+                first_node += len(a)
+            nbs.append((index, list(nb_min), nb_size, placed[k][0], placed[k][1], 0))
+    nb_arr = np.array(nbs, SeamNeighbour) if nbs else np.zeros(0, SeamNeighbour)
+    node_arr = np.concatenate(nodes) if nodes else np.zeros(0, SeamNodeInfo)
+    return jobs, nb_arr, node_arr
+
+
+def GenerateClipmapSeamMeshesPacked(voxelsPerChunk, jobs, nb_arr, node_arr, V=None, T=None):
+    """one lvn_seam_mesh_generate_batch call on packed arrays -> (rc, V, T, results)"""
+    cand = int(nb_arr["numNodes"].sum()) if len(nb_arr) else 0    # a node can be a vertex of several seams
+    vcap, tcap = max(cand, 1), max(8 * cand, 1)
+    V = np.zeros(vcap, MeshVertex) if V is None else V
+    T = np.zeros(tcap, MeshTriangle) if T is None else T
+    res = np.zeros(len(jobs), SeamResult)
+    rc = lib().lvn_seam_mesh_generate_batch(int(voxelsPerChunk), len(jobs), _ptr(jobs), _ptr(nb_arr), len(nb_arr), _ptr(node_arr),
+                                            len(node_arr), _ptr(V), len(V), _ptr(T), len(T), _ptr(res))
+    return rc, V, T, res
+
+
+def GenerateClipmapSeamMeshes(voxelsPerChunk, seams, colour=(1.0, 1.0, 1.0)):
+    """GenerateClipmapSeamMesh (clipmap.cpp:573-611) for a list of host nodes
+    -> (rc, [(vertices MeshVertex[], triangles MeshTriangle[]) per seam], results)"""
+    jobs, nb_arr, node_arr = PackSeamJobs(seams, colour)
+    rc, V, T, res = GenerateClipmapSeamMeshesPacked(voxelsPerChunk, jobs, nb_arr, node_arr)
+    meshes = [(V[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]].copy(),
+               T[r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]].copy()) for r in res]
+    return rc, meshes, res

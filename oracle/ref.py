@@ -364,3 +364,89 @@ class RefWorld:
             else:
                 edge_keys, edge_info = created, info
         return materials, edge_keys, edge_info
+
+
+# ---------------------------------------------------------------------------------------------
+# Seam meshes: the reference's seam octree (leven/src/octree.cpp, compiled
+# unmodified into oracle/_ref/libleven_octree_ref.so) behind the selection logic of clipmap.cpp.
+# ---------------------------------------------------------------------------------------------
+OCTREE_LIB_PATH = os.path.join(_HERE, "_ref", "libleven_octree_ref.so")
+CHILD_MIN_OFFSETS = [(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)]   # volume_constants.h:24-35
+_octree_lib = None
+
+
+def octree_available():
+    return os.path.exists(OCTREE_LIB_PATH)
+
+
+def octree_lib():
+    global _octree_lib
+    if _octree_lib is None:
+        if not octree_available():
+            raise ImportError(f"{OCTREE_LIB_PATH} is missing: `make -C oracle ref` (needs /root/reference)")
+        _octree_lib = C.CDLL(OCTREE_LIB_PATH)
+    return _octree_lib
+
+
+def filter_seam_node(child_index, seam_bounds, mn, mx):
+    """FilterSeamNode, clipmap.cpp:508-536"""
+    b = seam_bounds
+    if child_index == 0:
+        return mx[0] == b[0] or mx[1] == b[1] or mx[2] == b[2]
+    if child_index == 1:
+        return mn[2] == b[2]
+    if child_index == 2:
+        return mn[1] == b[1]
+    if child_index == 3:
+        return mn[1] == b[1] or mn[2] == b[2]
+    if child_index == 4:
+        return mn[0] == b[0]
+    if child_index == 5:
+        return mn[0] == b[0] or mn[2] == b[2]
+    if child_index == 6:
+        return mn[0] == b[0] or mn[1] == b[1]
+    if child_index == 7:
+        return mn[0] == b[0] and mn[1] == b[1] and mn[2] == b[2]
+    return False
+
+
+def select_seam_nodes(host_min, host_size, neighbours, V=64):
+    """GenerateMeshDataForNode's node construction (clipmap.cpp:398-415) + SelectSeamNodes
+    (clipmap.cpp:542-569) over the neighbour list of GenerateClipmapSeamMesh (clipmap.cpp:573-611).
+    neighbours: [(neighbourIndex 0..7, neighbourMin, neighbourSize, SeamNodeInfo array)].
+    Returns (minSize int[n][4], positions float[n][3], normals float[n][3], materialInfo int[n])."""
+    seam_bounds = [host_min[i] + host_size for i in range(3)]
+    lo, hi = list(host_min), [host_min[i] + 2 * host_size for i in range(3)]       # AABB(min, hostNodeSize * 2)
+    ms, pos, nrm, mat = [], [], [], []
+    for index, nb_min, nb_size, nodes in neighbours:
+        seam_node_size = nb_size // V                                              # clipmap.cpp:399
+        size = nb_size // (V * LEAF_SIZE_SCALE)                                    # clipmap.cpp:555
+        for nd in nodes:
+            lm = nd["localspaceMin"]
+            mn = [int(lm[i]) * seam_node_size + nb_min[i] for i in range(3)]
+            mx = [mn[i] + size * LEAF_SIZE_SCALE for i in range(3)]
+            inside = all(lo[i] <= mn[i] < hi[i] for i in range(3))                 # aabb.pointIsInside(node->min)
+            if not filter_seam_node(index, seam_bounds, mn, mx) or not inside:
+                continue
+            ms.append(mn + [seam_node_size])
+            pos.append([float(v) for v in nd["position"][:3]])
+            nrm.append([float(v) for v in nd["normal"][:3]])
+            mat.append(int(lm[3]))
+    return (np.array(ms, np.int32).reshape(-1, 4), np.array(pos, np.float32).reshape(-1, 3),
+            np.array(nrm, np.float32).reshape(-1, 3), np.array(mat, np.int32))
+
+
+def seam_mesh(host_min, host_size, neighbours, colour=(1.0, 1.0, 1.0), V=64):
+    """GenerateClipmapSeamMesh (clipmap.cpp:573-611): selection, Octree_ConstructUpwards over
+    (host min, 2 * host size), Octree_GenerateMesh.  Returns (vertices VERTEX_DTYPE[], triangles int[n][3])."""
+    ms, pos, nrm, mat = select_seam_nodes(host_min, host_size, neighbours, V)
+    n = len(ms)
+    verts = np.zeros(max(n, 1), VERTEX_DTYPE)
+    tris = np.zeros((max(4 * n, 1) * 3, 3), np.int32)
+    nv = C.c_int(0)
+    root = np.array(list(host_min), np.int32)
+    col = np.array(colour, np.float32)
+    rc = octree_lib().ref_seam_octree_mesh(n, _p(ms), _p(pos), _p(nrm), _p(mat), _p(root), int(2 * host_size), _p(col),
+                                           _p(verts), len(verts), C.byref(nv), _p(tris), len(tris))
+    assert rc >= 0, "seam mesh buffers too small"
+    return verts[:nv.value].copy() if rc > 0 else verts[:0].copy(), tris[:rc].copy()

@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """Make one of the reference's OpenCL C sources palatable to g++ (with clc.hpp), without changing
-what it computes.  Usage: translate.py <in.cl> <out.inc>
+what it computes.  Usage: translate.py <in> <out.inc> [--drop-include <header> ...]
 
 Only syntax that C++ cannot parse is rewritten; every expression, table and constant stays the
 reference's own text (a #line directive points compiler diagnostics back at it):
   (float4)(a, b, c, d)   ->  float4(a, b, c, d)        OpenCL vector literal -> constructor call
   #include "cl/x.glsl"   ->  #include "x.glsl.inc"     the translated copy next to this one
   #pragma OPENCL / unroll ->  dropped
+For the reference's C++ (leven/src/octree.cpp, the seam octree) nothing is rewritten at all;
+--drop-include removes #include lines of headers whose own includes cannot be satisfied here
+(window system, renderer, thread pool: render.h, volume.h, ...) -- the two functions and one
+constant octree.cpp takes from them are supplied by oracle/ref_shim/ref_octree.cpp.
 The output is a build intermediate under oracle/_ref/ (git-ignored, deleted after the build).
 """
 import os
@@ -14,7 +18,11 @@ import re
 import sys
 
 
-def translate(text, src_path):
+def translate(text, src_path, drop=()):
+    for h in drop:
+        text = re.sub(r'^[ \t]*#include\s+"%s".*$' % re.escape(h), "// (include of %s dropped)" % h, text, flags=re.M)
+    if src_path.endswith((".cpp", ".h")):
+        return '#line 1 "%s"\n%s\n' % (src_path, text)
     text = re.sub(r"\(\s*(float|int|uint)([234])\s*\)\s*\(", r"\1\2(", text)
     text = re.sub(r'#include\s+"cl/([A-Za-z0-9_.]+)"', r'#include "\1.inc"', text)
     text = re.sub(r"^\s*#pragma\s+(OPENCL|unroll).*$", "", text, flags=re.M)
@@ -23,7 +31,8 @@ def translate(text, src_path):
 
 if __name__ == "__main__":
     src, dst = sys.argv[1], sys.argv[2]
+    drop = [sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == "--drop-include"]
     with open(src, encoding="utf-8", errors="replace") as f:
-        out = translate(f.read(), os.path.abspath(src))
+        out = translate(f.read(), os.path.abspath(src), drop)
     with open(dst, "w") as f:
         f.write(out)

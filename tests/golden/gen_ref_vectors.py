@@ -131,5 +131,46 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_seams():
+    """tests/golden/ref_seams.npz: per scenario (tests/seam_scenarios.py) and host node, the
+    vertex / triangle counts and sha256 digests of the seam mesh the reference's octree.cpp
+    produces (oracle/_ref/libleven_octree_ref.so behind oracle/ref.py's selection)."""
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import seam_scenarios as S
+    from oracle import oracle as O, ref as R
+    assert R.build() and R.octree_available()
+    W = O.World(seed=SEED)
+    cy = int(900 * W.terrain(0.0, 0.0) // 64)
+    cache = {}
+
+    def seams_of(mn, size):
+        k = (tuple(mn), size)
+        if k not in cache:
+            r = W.generate_chunk_mesh(list(mn), size)
+            W.free_chunk_octree(list(mn), size)
+            cache[k] = r["seams"]
+        return cache[k]
+
+    def canon(t):
+        t = np.asarray(t, np.int32).reshape(-1, 3)
+        return t[np.lexsort((t[:, 2], t[:, 1], t[:, 0]))] if len(t) else t
+    out = {}
+    for name, make in S.SCENARIOS.items():
+        rows = []
+        for host, size, nbs in S.build_jobs(make(cy), seams_of):
+            v, t = R.seam_mesh(host, size, nbs)
+            rows.append([str(len(v)), str(len(t)), hashlib.sha256(v.tobytes()).hexdigest(), hashlib.sha256(canon(t).tobytes()).hexdigest()])
+        out[name] = np.array(rows)
+        print(name, len(rows), "seams", sum(int(r[0]) for r in rows), "vertices", sum(int(r[1]) for r in rows), "triangles")
+    path = os.path.join(ROOT, "tests", "golden", "ref_seams.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "seams":
+        main_seams()
+    else:
+        main()
+        main_seams()
