@@ -401,6 +401,7 @@ struct lvn_meshgen {
     DevBuf<unsigned int> d_bitsHi, d_rowE, d_rowN, d_rowQ, d_rowS;
     DevBuf<int> d_edgeKeys;
     DevBuf<float4> d_edgeInfo;
+    DevBuf<int2> d_xzList;         // (chunk, edge slot) of every x/z edge of a lane: the Hermite search list
     DevBuf<lvn_mesh_vertex> d_vertices;
     DevBuf<int> d_tris;
     DevBuf<lvn_seam_node_info> d_seams;
@@ -507,7 +508,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_colOrigins.release(); ctx->d_heights.release();
     ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
-    ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release();
+    ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release(); ctx->d_xzList.release();
     ctx->d_vertices.release(); ctx->d_tris.release(); ctx->d_seams.release();
     ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release();
     ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
@@ -694,8 +695,11 @@ static void choose_pipeline(const lvn_meshgen *ctx, int n, const BatchOpts &opts
     lanes = ctx->cfgLanes;
     streams = ctx->cfgStreams;
     if (lanes <= 0) {
-        lanes = n >= 128 ? (hostPath ? 4 : 2) : 1;
-        streams = hostPath ? 1 : 2;
+        // device-resident: 2 lanes x 2 streams; host path: 8 x 2 (the first copy starts after 1/8 of the
+        // batch; since the lane headers are published early a lane boundary costs ~1 us under D2H
+        // load, profiles/r01h_notes.md)
+        lanes = n >= 128 ? (hostPath ? 8 : 2) : 1;
+        streams = 2;
     }
     // per-stage event timing and the stage dumps want one kernel at a time on one stream
     if (ctx->profiling || opts.debug || opts.singleLane) lanes = 1;
@@ -821,6 +825,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     // first-guess arena sizes; a batch that needs more reports it in the counters and is re-run
     LV(ctx->d_edgeKeys.reserve(std::max<size_t>((size_t)n * 2048, 1u << 16)));
     LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
+    LV(ctx->d_xzList.reserve(ctx->d_edgeKeys.cap));
     LV(ctx->d_vertices.reserve(std::max<size_t>((size_t)n * 2048, 1u << 16)));
     LV(ctx->d_tris.reserve(ctx->d_vertices.cap * 6 * 2));
     LV(ctx->d_seams.reserve(std::max<size_t>((size_t)n * 512, 1u << 14)));
@@ -930,7 +935,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             {
                 StageTimer t(ctx, LVN_STAGE_HERMITE, 1);
                 launch_hermite(dp, d, ctx->d_descs.p, hdrs, ws, lane, ctx->d_heights.p, ctx->d_edgeKeys.p,
-                               ctx->d_edgeInfo.p, ls);
+                               ctx->d_edgeInfo.p, ctx->d_xzList.p, ls);
             }
             LVN_TRACE_EV(2);
             {
@@ -1044,6 +1049,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         // counters keep counting past the capacity, so one retry suffices
         LV(ctx->d_edgeKeys.reserve((size_t)S * ((size_t)mx.edges + mx.edges / 8 + 1024)));
         LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
+        LV(ctx->d_xzList.reserve(ctx->d_edgeKeys.cap));
         LV(ctx->d_vertices.reserve((size_t)S * ((size_t)mx.nodes + mx.nodes / 8 + 1024)));
         LV(ctx->d_tris.reserve((size_t)S * ((size_t)mx.quads + mx.quads / 8 + 1024) * 6));
         LV(ctx->d_seams.reserve((size_t)S * ((size_t)mx.seams + mx.seams / 8 + 1024)));

@@ -46,6 +46,7 @@ struct ArenaCounters {
     unsigned int overflow;
     unsigned int nonEmpty;
     unsigned int edgeTiles, nodeTiles;   // entries of the tile directories
+    unsigned int xzEdges;                // entries of the lane's x/z-edge search list (k_hermite_locate)
 };
 
 // Tile directories: the Hermite and leaf kernels run one block per tile of LVN_TILE consecutive
@@ -126,7 +127,7 @@ void launch_rows(const Dims &d, const ChunkDesc *descs, int first, int n, const 
 void launch_publish(const ChunkHdr *devHdrs, ChunkHdr *hostHdrs, int count, cudaStream_t s);
 void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
                     ChunkScratch ws, LaneArenas lane, const float *heights, int *edgeKeys, float4 *edgeInfo,
-                    cudaStream_t s);
+                    int2 *xzList, cudaStream_t s);
 void launch_leaves(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
                    ChunkScratch ws, LaneArenas lane, ArenaCounters *hostCounters, const float4 *edgeInfo,
                    lvn_mesh_vertex *vertices, int *triIndices, lvn_seam_node_info *seams,

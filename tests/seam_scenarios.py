@@ -59,7 +59,16 @@ def mixed_lod012(cy):
     return out
 
 
-SCENARIOS = {"uniform_lod0": uniform_lod0, "mixed_lod01": mixed_lod01, "mixed_lod012": mixed_lod012}
+def collision_nodes(cy):
+    """the collision feed (SURVEY.md 8f-4): Clipmap::loadCollisionNodes / GenerateCollisionSeamMesh
+    (clipmap.cpp:474-503,613-640) mesh nodes of COLLISION_NODE_SIZE = 512 world units with a 64-voxel
+    context (sampleScale 2) and stitch them with the same seam code, all neighbours at that one size"""
+    y1 = (cy * 256 // 512) * 512
+    return [((px, py, pz), 512) for px in (-1024, -512, 0, 512) for py in (y1 - 512, y1) for pz in (-1024, -512, 0, 512)]
+
+
+SCENARIOS = {"uniform_lod0": uniform_lod0, "mixed_lod01": mixed_lod01, "mixed_lod012": mixed_lod012,
+             "collision_nodes": collision_nodes}
 
 
 def build_jobs(active, seams_of):

@@ -131,3 +131,7 @@ def test_packed_fp32_is_not_contracted(built):
     assert cols[0]["FFMA2"] == 301 and cols[0]["FADD2"] == 360, cols[0]
     # two inlined evaluations (phase A, phase B)
     assert herm[0]["FFMA2"] >= 2 * 301 and herm[0]["FADD2"] == 2 * 360, herm[0]
+    # the split kernels: one evaluation each
+    for name in ("k_hermite_search", "k_hermite_normals"):
+        ks = [v for k, v in per_fn.items() if name in k]
+        assert len(ks) == 1 and ks[0]["FFMA2"] >= 301 and ks[0]["FADD2"] == 360, (name, ks)
