@@ -988,7 +988,9 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 if (c.quads) { dst[m] = out->triangles + ht; src[m] = ctx->d_tris.p + (size_t)b.quads * 6; len[m++] = (size_t)c.quads * 6 * sizeof(int); }
                 if (c.seams) { dst[m] = out->seams + hs; src[m] = ctx->d_seams.p + b.seams; len[m++] = (size_t)c.seams * sizeof(lvn_seam_node_info); }
 #if CUDART_VERSION >= 12080
-                if (m > 1) {
+                // (small single-lane batches usually land in pageable memory, where the batched call
+                // costs ~0.6 ms more than three plain copies: measured with config 3's re-meshes)
+                if (m > 1 && S > 1) {
                     cudaMemcpyAttributes attr = {};
                     attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
                     size_t attrIdx = 0, failIdx = 0;
