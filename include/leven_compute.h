@@ -257,6 +257,40 @@ int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, const lvn_sea
                                  lvn_seam_result *results);
 const char *lvn_seam_last_error(void);
 
+/* ---- mesh simplification (the pass over every chunk mesh right after export) --- */
+
+/* MeshSimplificationOptions, ng_mesh_simplify.h:6-28 */
+typedef struct lvn_simplify_options {
+    float   edgeFraction;       /* 0.125 */
+    int32_t maxIterations;      /* 10 */
+    float   targetPercentage;   /* 0.05 */
+    float   maxError;           /* 5 * leafSize at the clipmap's call site, clipmap.cpp:460 */
+    float   maxEdgeSize;        /* 2.5 * leafSize, clipmap.cpp:461 */
+    float   minAngleCosine;     /* options.h:16 = 0.7, clipmap.cpp:462 */
+} lvn_simplify_options;
+
+typedef struct lvn_simplify_job {
+    int32_t vertexOffset, numVertices;       /* the mesh's slices of the two arrays */
+    int32_t triangleOffset, numTriangles;    /* triangle indices are mesh-local */
+    float   worldSpaceOffset[4];             /* ngMeshSimplifier's argument: the node centre, w = 0 (clipmap.cpp:451) */
+} lvn_simplify_job;
+
+typedef struct lvn_simplify_result { int32_t numVertices, numTriangles, iterations, numEdges; } lvn_simplify_result;
+
+/* ngMeshSimplifier (ng_mesh_simplify.cpp:441-540) on many meshes in one launch, one thread block
+ * per mesh, in place: each mesh's simplified vertices / triangles are left at the start of its
+ * slices, results[m] holds the new counts.  Same vertices, same triangles, same order as the
+ * reference built with libstdc++ (its candidate sampling is std::uniform_int_distribution over
+ * std::mt19937(42), which is library-defined) and with _mm_rsqrt_ps taken as 1 / sqrt.
+ * A mesh holding a triangle index outside its vertices is passed through untouched with
+ * results[m].iterations = -1 and the call returns LVN_ERR_INVALID_VALUE (the other meshes are done). */
+int lvn_mesh_simplify_batch(int numMeshes, const lvn_simplify_job *jobs,
+                            const lvn_simplify_options *options, int numOptions,   /* 1 (shared) or numMeshes */
+                            lvn_mesh_vertex *vertices, int64_t numVerticesTotal,
+                            lvn_mesh_triangle *triangles, int64_t numTrianglesTotal,
+                            lvn_simplify_result *results);
+const char *lvn_mesh_simplify_last_error(void);
+
 /* ---- utilities of the path (a9, a15), usable on their own ---------------- */
 
 /* FindNextPrime, primes.h (primes.cpp:32-59) */

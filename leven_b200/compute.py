@@ -131,6 +131,8 @@ ABI = {
     "lvn_cuckoo_destroy": (None, [_P]),
     "lvn_seam_mesh_generate_batch": (_I, [_I, _I, _P, _P, _I, _P, _I, _P, _I64, _P, _I64, _P]),
     "lvn_seam_last_error": (C.c_char_p, []),
+    "lvn_mesh_simplify_batch": (_I, [_I, _P, _P, _I, _P, _I64, _P, _I64, _P]),
+    "lvn_mesh_simplify_last_error": (C.c_char_p, []),
 }
 
 _lib = None
@@ -539,3 +541,77 @@ def GenerateClipmapSeamMeshes(voxelsPerChunk, seams, colour=(1.0, 1.0, 1.0)):
     meshes = [(V[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]].copy(),
                T[r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]].copy()) for r in res]
     return rc, meshes, res
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh simplification (ngMeshSimplifier, ng_mesh_simplify.cpp:441-540)
+# ---------------------------------------------------------------------------------------------
+SimplifyJob = np.dtype([("vertexOffset", np.int32), ("numVertices", np.int32), ("triangleOffset", np.int32),
+                        ("numTriangles", np.int32), ("worldSpaceOffset", np.float32, 4)])
+SimplifyResult = np.dtype([("numVertices", np.int32), ("numTriangles", np.int32), ("iterations", np.int32), ("numEdges", np.int32)])
+
+
+class SimplifyOptions(C.Structure):
+    """MeshSimplificationOptions, ng_mesh_simplify.h:6-28"""
+    _fields_ = [("edgeFraction", C.c_float), ("maxIterations", C.c_int32), ("targetPercentage", C.c_float),
+                ("maxError", C.c_float), ("maxEdgeSize", C.c_float), ("minAngleCosine", C.c_float)]
+
+    @classmethod
+    def for_clipmap_node(cls, node_size):
+        """ConstructClipmapNodeData, clipmap.cpp:449-465 (options.h:14-16)"""
+        leaf = float(4 * (node_size // 256))
+        return cls(0.125, 10, 0.05, 5.0 * leaf, 2.5 * leaf, 0.7)
+
+
+    @classmethod
+    def make(cls, **kw):
+        """the struct's defaults (ng_mesh_simplify.h:6-28) with overrides"""
+        d = dict(edgeFraction=0.125, maxIterations=10, targetPercentage=0.05, maxError=5.0, maxEdgeSize=2.5, minAngleCosine=0.8)
+        d.update(kw)
+        return cls(d["edgeFraction"], d["maxIterations"], d["targetPercentage"], d["maxError"], d["maxEdgeSize"], d["minAngleCosine"])
+
+
+def PackSimplifyMeshes(meshes):
+    """[(vertices, triangles MeshTriangle[] or int[n][3], worldSpaceOffset xyz)] -> (jobs SimplifyJob[],
+    V MeshVertex[], T MeshTriangle[]): the packed arrays lvn_mesh_simplify_batch works on in place"""
+    jobs = np.zeros(len(meshes), SimplifyJob)
+    vo = to = 0
+    for m, (v, t, off) in enumerate(meshes):
+        nt = len(t) if isinstance(t, np.ndarray) and t.dtype == MeshTriangle else len(np.asarray(t).reshape(-1)) // 3
+        jobs[m] = (vo, len(v), to, nt, list(off)[:3] + [0.0])
+        vo += len(v); to += nt
+    V = np.zeros(max(vo, 1), MeshVertex)
+    T = np.zeros(max(to, 1), MeshTriangle)
+    for j, (v, t, off) in zip(jobs, meshes):
+        for f in ("xyz", "normal", "colour"):
+            V[f][j["vertexOffset"]:j["vertexOffset"] + j["numVertices"]] = v[f]
+        tt = t["indices_"] if isinstance(t, np.ndarray) and t.dtype == MeshTriangle else np.asarray(t, np.int32).reshape(-1, 3)
+        T["indices_"][j["triangleOffset"]:j["triangleOffset"] + j["numTriangles"]] = tt
+    return jobs, V, T
+
+
+def ngMeshSimplifierPacked(jobs, options, V, T):
+    """lvn_mesh_simplify_batch on packed arrays, in place -> (rc, results SimplifyResult[]);
+    options: one SimplifyOptions for all, or a list with one per mesh"""
+    res = np.zeros(len(jobs), SimplifyResult)
+    if isinstance(options, SimplifyOptions):
+        oarr, nopt = (SimplifyOptions * 1)(options), 1
+    else:
+        assert len(options) == len(jobs)
+        oarr, nopt = (SimplifyOptions * max(len(options), 1))(*options), len(options)
+    nv = int(jobs["vertexOffset"][-1] + jobs["numVertices"][-1]) if len(jobs) else 0
+    nt = int(jobs["triangleOffset"][-1] + jobs["numTriangles"][-1]) if len(jobs) else 0
+    rc = lib().lvn_mesh_simplify_batch(len(jobs), _ptr(jobs), oarr, nopt, _ptr(V), nv, _ptr(T), nt, _ptr(res))
+    return rc, res
+
+
+def ngMeshSimplifierBatch(meshes, options):
+    """ngMeshSimplifier (ng_mesh_simplify.cpp:441-540) over many meshes in one launch.
+    meshes: [(vertices MeshVertex[], triangles MeshTriangle[] or int[n][3], worldSpaceOffset xyz)];
+    options: one SimplifyOptions for all, or a list with one per mesh (they scale with the node size)
+    -> (rc, [(vertices, triangles) simplified], results)"""
+    jobs, V, T = PackSimplifyMeshes(meshes)
+    rc, res = ngMeshSimplifierPacked(jobs, options, V, T)
+    out = [(V[j["vertexOffset"]:j["vertexOffset"] + r["numVertices"]].copy(),
+            T[j["triangleOffset"]:j["triangleOffset"] + r["numTriangles"]].copy()) for j, r in zip(jobs, res)]
+    return rc, out, res

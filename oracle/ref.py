@@ -450,3 +450,57 @@ def seam_mesh(host_min, host_size, neighbours, colour=(1.0, 1.0, 1.0), V=64):
                                            _p(verts), len(verts), C.byref(nv), _p(tris), len(tris))
     assert rc >= 0, "seam mesh buffers too small"
     return verts[:nv.value].copy() if rc > 0 else verts[:0].copy(), tris[:rc].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Mesh simplification: the reference's ng_mesh_simplify.cpp + qef_simd.h compiled
+# into oracle/_ref/libleven_simplify_ref.so (see ref_shim/ref_simplify.cpp for what the shim defines)
+# ---------------------------------------------------------------------------------------------
+SIMPLIFY_LIB_PATH = os.path.join(_HERE, "_ref", "libleven_simplify_ref.so")
+_simplify_lib = None
+# MeshSimplificationOptions defaults (ng_mesh_simplify.h:6-28) with the values the clipmap passes at
+# LOD0 (clipmap.cpp:449-465, options.h:14-16): maxError 5 * leafSize, maxEdgeSize 2.5 * leafSize,
+# minAngleCosine 0.7, leafSize = LEAF_SIZE_SCALE * size / CLIPMAP_LEAF_SIZE
+SIMPLIFY_DEFAULTS = dict(edgeFraction=0.125, maxIterations=10, targetPercentage=0.05, maxError=5.0, maxEdgeSize=2.5,
+                         minAngleCosine=0.8)
+
+
+def simplify_available():
+    return os.path.exists(SIMPLIFY_LIB_PATH)
+
+
+def simplify_lib():
+    global _simplify_lib
+    if _simplify_lib is None:
+        if not simplify_available():
+            raise ImportError(f"{SIMPLIFY_LIB_PATH} is missing: `make -C oracle ref` (needs /root/reference)")
+        _simplify_lib = C.CDLL(SIMPLIFY_LIB_PATH)
+    return _simplify_lib
+
+
+def clipmap_simplify_options(node_size):
+    """ConstructClipmapNodeData, clipmap.cpp:449-465"""
+    leaf = float(LEAF_SIZE_SCALE * (node_size // CLIPMAP_LEAF_SIZE))
+    o = dict(SIMPLIFY_DEFAULTS)
+    o.update(maxError=5.0 * leaf, maxEdgeSize=2.5 * leaf, minAngleCosine=0.7)
+    return o
+
+
+def simplify_mesh(vertices, triangles, world_space_offset, options):
+    """ngMeshSimplifier (ng_mesh_simplify.cpp:441-540) -> (vertices VERTEX_DTYPE[], triangles int[n][3])"""
+    v = np.array(vertices, VERTEX_DTYPE)
+    t = np.ascontiguousarray(np.asarray(triangles, np.int32).reshape(-1, 3)).copy()
+    nv, nt = C.c_int(len(v)), C.c_int(len(t))
+    off = np.array(list(world_space_offset)[:3] + [0.0], np.float32)
+    f = C.c_float
+    rc = simplify_lib().ref_mesh_simplify(_p(v), C.byref(nv), _p(t), C.byref(nt), _p(off), f(options["edgeFraction"]),
+                                          int(options["maxIterations"]), f(options["targetPercentage"]), f(options["maxError"]),
+                                          f(options["maxEdgeSize"]), f(options["minAngleCosine"]))
+    assert rc == 0, "mesh exceeds the reference's MeshBuffer capacity"
+    return v[:nv.value].copy(), t[:nt.value].copy()
+
+
+def random_edges(num_edges, count):
+    out = np.zeros(count, np.int32)
+    simplify_lib().ref_random_edges(int(num_edges), int(count), _p(out))
+    return out

@@ -30,7 +30,7 @@ template <class T> struct tvec3 {
     T &operator[](int i) { return (&x)[i]; }
     const T &operator[](int i) const { return (&x)[i]; }
 };
-template <class T> struct tvec4 {
+template <class T> struct alignas(16) tvec4 {   // 16-byte aligned: the simplifier _mm_load_ps's MeshVertex members
     T x, y, z, w;
     tvec4() : x(0), y(0), z(0), w(0) {}
     explicit tvec4(T s) : x(s), y(s), z(s), w(s) {}
@@ -85,6 +85,8 @@ template <class T> tvec3<T> max(const tvec3<T> &a, const tvec3<T> &b) { return t
 inline float dot(const vec3 &a, const vec3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline float dot(const vec4 &a, const vec4 &b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 inline float length(const vec3 &a) { return std::sqrt(dot(a, a)); }
+inline float length2(const vec3 &a) { return dot(a, a); }   // gtx/norm.inl
+inline float length2(const vec4 &a) { return dot(a, a); }
 inline vec3 normalize(const vec3 &a) { return a * (1.f / length(a)); }
 inline vec3 cross(const vec3 &a, const vec3 &b) { return vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 inline int log2(int v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }

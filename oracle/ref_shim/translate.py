@@ -22,6 +22,8 @@ def translate(text, src_path, drop=()):
     for h in drop:
         text = re.sub(r'^[ \t]*#include\s+"%s".*$' % re.escape(h), "// (include of %s dropped)" % h, text, flags=re.M)
     if src_path.endswith((".cpp", ".h")):
+        # MSVC's __m128 is a union with a float array member, gcc's is a vector type: x.m128_f32[i] -> x[i]
+        text = re.sub(r"\.m128_f32\s*\[", "[", text)
         return '#line 1 "%s"\n%s\n' % (src_path, text)
     text = re.sub(r"\(\s*(float|int|uint)([234])\s*\)\s*\(", r"\1\2(", text)
     text = re.sub(r'#include\s+"cl/([A-Za-z0-9_.]+)"', r'#include "\1.inc"', text)

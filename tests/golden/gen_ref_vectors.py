@@ -168,9 +168,40 @@ def main_seams():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_simplify():
+    """tests/golden/ref_simplify.npz: per case of tests/simplify_scenarios.py, the input's and the
+    output's vertex / triangle counts and sha256 digests, the output being what the reference's
+    ng_mesh_simplify.cpp + qef_simd.h produce (oracle/_ref/libleven_simplify_ref.so; see
+    oracle/ref_shim/ref_simplify.cpp for the two platform-defined pieces it has to fix)."""
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import simplify_scenarios as S
+    from oracle import oracle as O, ref as R
+    assert R.build() and R.simplify_available()
+    W, W2 = O.World(seed=SEED), O.World(seed=SEED)
+    cy = int(900 * W.terrain(0.0, 0.0) // 64)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    names, rows = [], []
+    for name, v, t, off, opt in S.all_cases(W, O, cy, W2):
+        vin = S.as_vertices(v)
+        rv, rt = R.simplify_mesh(vin, t, off, opt)
+        names.append(name)
+        rows.append([str(len(vin)), str(len(t)), sha(vin), sha(np.asarray(t, np.int32)), str(len(rv)), str(len(rt)), sha(rv), sha(rt)])
+        print(name, len(vin), len(t), "->", len(rv), len(rt))
+    # the candidate sample itself (libstdc++'s uniform_int_distribution over mt19937(42)) for a few ranges
+    out = {"cases": np.array(names), "rows": np.array(rows)}
+    for n in (7, 1000, 16944, 86016, (1 << 20) + 3):
+        out[f"random_edges/{n}"] = R.random_edges(n, 4096)
+    path = os.path.join(ROOT, "tests", "golden", "ref_simplify.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "seams":
-        main_seams()
-    else:
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("chunks", "all"):
         main()
+    if which in ("seams", "all"):
         main_seams()
+    if which in ("simplify", "all"):
+        main_simplify()
