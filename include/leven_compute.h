@@ -291,6 +291,23 @@ int lvn_mesh_simplify_batch(int numMeshes, const lvn_simplify_job *jobs,
                             lvn_simplify_result *results);
 const char *lvn_mesh_simplify_last_error(void);
 
+/* ConstructClipmapNodeData / ConstructCollisionNodeData (clipmap.cpp:432-504) for many nodes in one
+ * pass: generateChunkMesh, then ngMeshSimplifier with worldSpaceOffset = min + size / 2 and
+ * options scaled by the node's leaf size (leafSize = LEAF_SIZE_SCALE * (size / CLIPMAP_LEAF_SIZE);
+ * maxError = unitOptions->maxError * leafSize, maxEdgeSize likewise; unitOptions carries
+ * Options::meshMaxError_ / meshMaxEdgeLen_ / meshMinCosAngle_, options.h:14-16).  The meshes never
+ * leave HBM between the two steps; the host arenas receive the SIMPLIFIED meshes, densely packed in
+ * chunk order, and the (unsimplified octree's) seam nodes.  results[i] addresses chunk i's slices
+ * and holds the simplified counts (numEdges stays the chunk's Hermite edge count); simplified[i]
+ * (may be NULL) adds the simplifier's iteration count (-2: the mesh was too large to simplify and
+ * is returned as generated).  On LVN_ERR_CAPACITY the counts say what the caller must provide. */
+int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                          const lvn_simplify_options *unitOptions,
+                                          lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                          lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                          lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                          lvn_chunk_result *results, lvn_simplify_result *simplified);
+
 /* ---- utilities of the path (a9, a15), usable on their own ---------------- */
 
 /* FindNextPrime, primes.h (primes.cpp:32-59) */

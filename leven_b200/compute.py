@@ -133,6 +133,7 @@ ABI = {
     "lvn_seam_last_error": (C.c_char_p, []),
     "lvn_mesh_simplify_batch": (_I, [_I, _P, _P, _I, _P, _I64, _P, _I64, _P]),
     "lvn_mesh_simplify_last_error": (C.c_char_p, []),
+    "lvn_meshgen_generate_simplified_batch": (_I, [_P, _I, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
 }
 
 _lib = None
@@ -316,6 +317,20 @@ class Compute_MeshGenContext:
         rc = self._L.lvn_meshgen_generate_batch_device(self.privateCtx_, len(ms), _ptr(ms), _ptr(results),
                                                        C.byref(view))
         return rc, results, view
+
+    def generateSimplifiedBatch(self, chunkMinSize, vertices, triangles, seamNodes, unitOptions=None):
+        """ConstructClipmapNodeData (clipmap.cpp:432-468) over a batch: generateChunkMesh + ngMeshSimplifier,
+        the meshes staying in HBM between the two; host arenas receive the simplified meshes.
+        unitOptions: SimplifyOptions whose maxError / maxEdgeSize are per leaf size (options.h:14-16).
+        Returns (error, results ChunkResult[], simplified SimplifyResult[])"""
+        ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
+        results = np.zeros(len(ms), ChunkResult)
+        simp = np.zeros(len(ms), SimplifyResult)
+        opt = unitOptions if unitOptions is not None else SimplifyOptions.clipmap_unit()
+        rc = self._L.lvn_meshgen_generate_simplified_batch(self.privateCtx_, len(ms), _ptr(ms), C.byref(opt),
+                                                           _ptr(vertices), len(vertices), _ptr(triangles), len(triangles),
+                                                           _ptr(seamNodes), len(seamNodes), _ptr(results), _ptr(simp))
+        return rc, results, simp
 
     def applyCSGOperationsBatch(self, opInfo, chunkMinSize):
         ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
@@ -562,6 +577,11 @@ class SimplifyOptions(C.Structure):
         leaf = float(4 * (node_size // 256))
         return cls(0.125, 10, 0.05, 5.0 * leaf, 2.5 * leaf, 0.7)
 
+
+    @classmethod
+    def clipmap_unit(cls):
+        """Options::meshMaxError_ / meshMaxEdgeLen_ / meshMinCosAngle_ (options.h:14-16), before the leaf-size scaling"""
+        return cls(0.125, 10, 0.05, 5.0, 2.5, 0.7)
 
     @classmethod
     def make(cls, **kw):

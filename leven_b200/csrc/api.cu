@@ -420,6 +420,13 @@ struct lvn_meshgen {
     DevBuf<unsigned int> d_touched, d_csgCounts;
     DevBuf<CsgOpDev> d_ops;
     DevBuf<CsgChunk> d_csgChunks;
+    // simplified batch (lvn_meshgen_generate_simplified_batch)
+    DevBuf<int4> d_simpRes;
+    DevBuf<int2> d_packOff;
+    DevBuf<lvn_mesh_vertex> d_packV;
+    DevBuf<int> d_packT;
+    PinBuf<int4> h_simpRes;
+    PinBuf<int2> h_packOff;
 
     PinBuf<ChunkDesc> h_descs;
     PinBuf<ChunkHdr> h_hdrs;
@@ -1123,6 +1130,94 @@ extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const i
         if (ctx && ctx->numLanes) fill_results(ctx, nChunks, results);
     }
     return rc;
+}
+
+// ConstructClipmapNodeData / ConstructCollisionNodeData (clipmap.cpp:432-504) for many nodes:
+// generateChunkMesh, then ngMeshSimplifier with the options the clipmap derives from the node size.
+// The meshes stay in HBM between the two; only the simplified meshes cross PCIe.
+extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                                     const lvn_simplify_options *unitOptions,
+                                                     lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                                     lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                                     lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                                     lvn_chunk_result *results, lvn_simplify_result *simplified)
+{
+    if (!results || !unitOptions) return LVN_ERR_INVALID_VALUE;
+    BatchOpts opts;
+    LV(run_batch(ctx, nChunks, chunkMinSize, opts));
+    if (nChunks == 0) return LVN_SUCCESS;
+    fill_results(ctx, nChunks, results);      // offsets into the device arenas
+    cudaStream_t st = ctx->stream;
+
+    std::vector<SimplifyMesh> meshes;
+    std::vector<int> chunkOf;
+    meshes.reserve(ctx->lastCounters.nonEmpty);
+    for (int i = 0; i < nChunks; i++) {
+        const lvn_chunk_result &r = results[i];
+        if (simplified) simplified[i] = lvn_simplify_result{0, 0, 0, 0};
+        if (r.status < 0 || r.numTriangles <= 0) continue;
+        const int32_t *ms = chunkMinSize + 4 * (size_t)i;
+        SimplifyMesh m;
+        m.vertexOffset = r.vertexOffset; m.numVertices = r.numVertices;
+        m.triangleOffset = r.triangleOffset; m.numTriangles = r.numTriangles;
+        // centrePos = vec4(vec3(min) + vec3(size / 2.f), 0); leafSize = LEAF_SIZE_SCALE * (size / CLIPMAP_LEAF_SIZE)
+        for (int a = 0; a < 3; a++) m.offset[a] = (float)ms[a] + (float)ms[3] / 2.f;
+        m.offset[3] = 0.f;
+        const float leafSize = (float)(LVN_LEAF_SIZE_SCALE * (ms[3] / (LVN_LEAF_SIZE_SCALE * 64)));
+        m.opt = *unitOptions;
+        m.opt.maxError = unitOptions->maxError * leafSize;
+        m.opt.maxEdgeSize = unitOptions->maxEdgeSize * leafSize;
+        meshes.push_back(m);
+        chunkOf.push_back(i);
+    }
+    const int M = (int)meshes.size();
+    const int64_t totalSeams = ctx->lastCounters.seams;
+    int2 totals = make_int2(0, 0);
+    if (M > 0) {
+        LV(ctx->d_simpRes.reserve(M));
+        LV(ctx->d_packOff.reserve((size_t)M + 1));
+        LV(ctx->d_packV.reserve(ctx->lastCounters.nodes));
+        LV(ctx->d_packT.reserve(6 * (size_t)ctx->lastCounters.quads));
+        LV(ctx->h_simpRes.reserve(M));
+        LV(ctx->h_packOff.reserve((size_t)M + 1));
+        const int rc = simplify_device(M, meshes.data(), ctx->d_vertices.p, ctx->d_tris.p, ctx->d_simpRes.p,
+                                       ctx->d_packV.p, ctx->d_packT.p, ctx->d_packOff.p, ctx->d_packOff.p + M, st);
+        if (rc < 0) { g_lastCudaError = simplify_last_error(); return rc; }
+        CU(cudaMemcpyAsync(ctx->h_simpRes.p, ctx->d_simpRes.p, sizeof(int4) * M, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_packOff.p, ctx->d_packOff.p, sizeof(int2) * ((size_t)M + 1), cudaMemcpyDeviceToHost, st));
+    }
+    // the seam nodes do not wait for the simplifier: lane by lane (each lane's slice is dense)
+    const bool seamsFit = totalSeams <= seamCapacity && (seamNodes || totalSeams == 0);
+    int64_t hs = 0;
+    for (int k = 0; k < ctx->numLanes; k++) {
+        const unsigned int cnt = ctx->laneCounters[k].seams;
+        ctx->hostBase[k][2] = hs;
+        if (seamsFit && cnt)
+            CU(cudaMemcpyAsync(seamNodes + hs, ctx->d_seams.p + ctx->laneBase[k].seams, sizeof(lvn_seam_node_info) * cnt, cudaMemcpyDeviceToHost, st));
+        hs += cnt;
+    }
+    CU(cudaStreamSynchronize(st));
+    if (M > 0) totals = ctx->h_packOff.p[M];
+    for (int k = 0; k < ctx->numLanes; k++)
+        for (int p = ctx->laneFirst[k]; p < ctx->laneFirst[k + 1]; p++) {
+            const ChunkHdr &h = ctx->h_hdrs.p[p + k];
+            results[ctx->perm[p]].seamOffset = (int32_t)(ctx->hostBase[k][2] + (h.S ? h.seamBase - (int)ctx->laneBase[k].seams : 0));
+        }
+    for (int i = 0; i < nChunks; i++) { results[i].vertexOffset = 0; results[i].triangleOffset = 0; }
+    for (int m = 0; m < M; m++) {
+        lvn_chunk_result &r = results[chunkOf[m]];
+        const int4 sr = ctx->h_simpRes.p[m];
+        r.numVertices = sr.x; r.numTriangles = sr.y;
+        r.vertexOffset = ctx->h_packOff.p[m].x; r.triangleOffset = ctx->h_packOff.p[m].y;
+        if (simplified) simplified[chunkOf[m]] = lvn_simplify_result{sr.x, sr.y, sr.z, sr.w};
+    }
+    // on LVN_ERR_CAPACITY the counts say what the caller must provide
+    if (!seamsFit || totals.x > vertexCapacity || totals.y > triangleCapacity ||
+        (totals.x > 0 && !vertices) || (totals.y > 0 && !triangles)) return LVN_ERR_CAPACITY;
+    if (totals.x) CU(cudaMemcpyAsync(vertices, ctx->d_packV.p, sizeof(lvn_mesh_vertex) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
+    if (totals.y) CU(cudaMemcpyAsync(triangles, ctx->d_packT.p, 12 * (size_t)totals.y, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return LVN_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------

@@ -171,4 +171,18 @@ void launch_fma_peak(float *sink, int iters, int blocks, cudaStream_t s);
 void launch_dedupe(const int *values, int count, unsigned int *table, unsigned int tableSize,
                    int *out, unsigned int *outCount, cudaStream_t s);
 
+// ---- simplify.cu: ngMeshSimplifier on device-resident meshes ----------------
+struct SimplifyMesh {
+    int vertexOffset, numVertices;       // the mesh's slices of the arrays below
+    int triangleOffset, numTriangles;
+    float offset[4];                     // worldSpaceOffset
+    lvn_simplify_options opt;
+};
+// in place, asynchronous on `st`; d_results[m] = (vertices, triangles, iterations, edges left);
+// iterations -1: a wild triangle index, -2: too large; both leave the mesh untouched.
+// With d_packV / d_packT the simplified meshes are also gathered densely in mesh order.
+int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int *d_T, int4 *d_results,
+                    lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st);
+const char *simplify_last_error();
+
 }  // namespace lvn

@@ -5,22 +5,28 @@
 // The reference's algorithm is already iteration-parallel in spirit (random candidate edges, each
 // vertex keeps its cheapest collapse, an edge collapses when both ends chose it); its loops are
 // sequential only in how they compact.  Here one thread block owns one mesh (a batch of meshes is
-// one launch) and every sequential loop becomes a block-wide pass with the same result:
-//   BuildCandidateEdges   std::sort by (max, min) -> counting sort by max vertex + a tiny sort of each
-//                         vertex's bucket by min; duplicate runs, boundary marks and the stable filter
-//                         by scans.  (The reference never flushes the last run of its scan: the
-//                         greatest edge is neither a candidate nor a boundary mark.  Kept.)
+// one launch), the mesh is simplified IN PLACE in its slices of the device arrays, and every
+// sequential loop becomes a block-wide pass with the same result:
+//   BuildCandidateEdges   std::sort by (max, min) -> counting sort by max vertex, then a rank sort
+//                         inside each vertex's bucket (one thread per raw edge, independent loads);
+//                         duplicate runs, boundary marks and the stable filter from neighbours in
+//                         the sorted list.  (The reference never flushes the last run of its scan:
+//                         the greatest edge is neither a candidate nor a boundary mark.  Kept.)
 //   FindValidCollapses    the candidate sample is std::mt19937(42) through libstdc++'s
 //                         std::uniform_int_distribution (Lemire multiply-shift with rejection),
 //                         reproduced from the precomputed raw stream; "first cheapest edge wins" in
 //                         ascending edge order = atomicMin on (error bits, edge index)
 //   CollapseEdges         one thread per vertex; the winner re-solves its 2-point QEF
-//   RemoveTriangles / RemoveEdges / CompactVertices   remap + stable compaction (scan + scatter)
+//   RemoveTriangles / RemoveEdges / CompactVertices   stable compaction
+// Stable compaction = warp ballots into shared-memory mask words, one scan of the words' popcounts,
+// destination = word prefix + popc(mask below my lane): two passes over the data and a handful of
+// block barriers per compaction, nothing written but the survivors.
 // The 4-D QEF solve restates qef_simd.h lane by lane, including what look like slips in
 // rotateq_xy (vtav[0][0] written twice, `cc + v`): the reference's results are the bar.
 // _mm_rsqrt_ps := 1 / sqrt(x) (arithmetic spec; the x86 estimate differs between CPU vendors).
 #include <algorithm>
 #include <cstring>
+#include <numeric>
 #include <random>
 #include <vector>
 
@@ -29,55 +35,105 @@
 namespace lvn {
 
 constexpr int SIMP_BLOCK = 512;
-constexpr int SIMP_RAW = 1 << 17;        // raw mt19937(42) outputs kept on the device
+constexpr int SIMP_WARPS = SIMP_BLOCK / 32;
 constexpr int SIMP_MAX_DEGREE = 16;      // COLLAPSE_MAX_DEGREE
-
-struct SimpOptionsDev { float edgeFraction; int maxIterations; float targetPercentage, maxError, maxEdgeSize, minAngleCosine; };
+constexpr int SIMP_SLACK = 256;          // raw draws beyond numRandom that one iteration may consume on rejections
+constexpr size_t SIMP_MAX_SMEM = 200 * 1024;
 
 struct SimpJobDev {
-    int vertexOffset, numVertices;       // into the packed input arrays
+    int vertexOffset, numVertices;       // the mesh's slices of the vertex / triangle arrays
     int triangleOffset, numTriangles;
     float offset[4];                     // worldSpaceOffset
-    SimpOptionsDev opt;                  // this mesh's options (they scale with the node's leaf size, clipmap.cpp:455-462)
-    // scratch slices (element offsets)
-    long long edgeOff;                   // capacity 3 * numTriangles (x2 buffers, bucket, flags)
+    lvn_simplify_options opt;            // this mesh's options (they scale with the node's leaf size, clipmap.cpp:455-462)
+    long long edgeOff;                   // scratch slices (element offsets): capacity 3 * numTriangles
     int vtxOff;                          // capacity numVertices
+    int result;                          // where this mesh's result goes (jobs are launched largest first)
+    int skip;                            // too large for this launch's shared-memory masks: reported, left untouched
 };
 
 struct SimpScratch {
     float4 *vx, *vn, *vc;                // working vertices
-    int *tri[2];                         // triangle ping-pong, 3 ints each
+    int *tri1;                           // the second triangle buffer (the first is the mesh's own slice), 3 ints each
     uint2 *edge[2];                      // (min, max) ping-pong
-    unsigned int *bucket;                // per raw edge: min, grouped by max
-    int *eflag, *escan;                  // per edge / triangle flags and scans
     int *vcount, *vstart, *vfill;        // per vertex: bucket count / start / cursor, later triangle counts
-    int *boundary, *target, *vflag, *vscan;
+    int *boundary, *target, *vscan;
     unsigned long long *best;            // per vertex (error bits << 32 | edge)
     const unsigned int *raw;             // mt19937(42) outputs
+    int maskWords;                       // capacity of each of the two shared-memory word arrays
 };
 
-// ---- block-wide exclusive scan of n ints in global memory (in -> out), returns the total ----
-__device__ int block_scan(const int *in, int *out, int n, int *s_warp, int *s_run)
+extern __shared__ unsigned int s_dyn[];  // [maskWords] ballot masks, [maskWords] exclusive prefix of their popcounts
+
+// exclusive prefix of the popcounts of s_mask[0 .. nwords) into s_pref; returns the total (same in every thread)
+__device__ __forceinline__ int words_prefix(const unsigned int *s_mask, int *s_pref, int nwords, int *s_warp)
 {
-    const int tid = threadIdx.x;
-    if (tid == 0) *s_run = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += SIMP_BLOCK) {
-        const int i = base + tid;
-        const int v = i < n ? in[i] : 0;
-        int incl = v;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < nwords; base += SIMP_BLOCK) {
+        const int w = base + tid;
+        const int c = w < nwords ? __popc(s_mask[w]) : 0;
+        int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
-        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        int woff = 0;
-        for (int w = 0; w < (tid >> 5); w++) woff += s_warp[w];
-        if (i < n) out[i] = *s_run + woff + incl - v;
-        __syncthreads();
-        if (tid == SIMP_BLOCK - 1) *s_run += woff + incl;
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int q = 0; q < SIMP_WARPS; q++) { const int v = s_warp[q]; if (q < warp) woff += v; tot += v; }
+        if (w < nwords) s_pref[w] = carry + woff + incl - c;
+        carry += tot;
         __syncthreads();
     }
-    return *s_run;
+    return carry;
+}
+
+// block-wide exclusive scan of n ints in global memory (in -> out, may alias), four per thread per round;
+// returns the total (same in every thread)
+__device__ __forceinline__ int block_scan(const int *in, int *out, int n, int *s_warp)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += SIMP_BLOCK * 4) {
+        const int i = base + tid * 4;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = i + k < n ? in[i + k] : 0;
+        const int sum = v[0] + v[1] + v[2] + v[3];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int q = 0; q < SIMP_WARPS; q++) { const int t = s_warp[q]; if (q < warp) woff += t; tot += t; }
+        int run = carry + woff + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (i + k < n) out[i + k] = run; run += v[k]; }
+        carry += tot;
+        __syncthreads();
+    }
+    return carry;
+}
+
+// pass 1 of a stable compaction: s_mask[i / 32] bit (i % 32) = pred(i), i < n
+template <class Pred>
+__device__ __forceinline__ void ballot_pass(int n, unsigned int *s_mask, Pred pred)
+{
+    const int tid = threadIdx.x;
+    const int nr = (n + 31) & ~31;
+#pragma unroll 2
+    for (int i = tid; i < nr; i += SIMP_BLOCK) {
+        const bool p = i < n && pred(i);
+        const unsigned int m = __ballot_sync(0xffffffffu, p);
+        if ((tid & 31) == 0) s_mask[i >> 5] = m;
+    }
+}
+// pass 2: where element i goes, or -1
+__device__ __forceinline__ int compact_slot(const unsigned int *s_mask, const int *s_pref, int i)
+{
+    const unsigned int m = s_mask[i >> 5], bit = 1u << (i & 31);
+    return (m & bit) ? s_pref[i >> 5] + __popc(m & (bit - 1u)) : -1;
 }
 
 // ---- qef_simd.h, lane by lane -------------------------------------------------------------
@@ -253,117 +309,118 @@ __device__ __forceinline__ float dot4_lr(const float4 a, const float4 b)   // GL
     return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }
 
-__global__ void __launch_bounds__(SIMP_BLOCK)
-k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws,
-           const lvn_mesh_vertex *__restrict__ inV, const int *__restrict__ inT,
-           lvn_mesh_vertex *__restrict__ outV, int *__restrict__ outT, int4 *__restrict__ results)
-{
-    __shared__ int s_warp[SIMP_BLOCK / 32], s_run, s_cnt, s_last[2], s_bad;
-    const SimpJobDev job = jobs[blockIdx.x];
-    const SimpOptionsDev opt = job.opt;
-    const int tid = threadIdx.x, NV = job.numVertices, NT0 = job.numTriangles;
-    const lvn_mesh_vertex *srcV = inV + job.vertexOffset;
-    const int *srcT = inT + (size_t)job.triangleOffset * 3;
-    lvn_mesh_vertex *dstV = outV + job.vertexOffset;
-    int *dstT = outT + (size_t)job.triangleOffset * 3;
+__device__ __forceinline__ void raw_edge(const int *tri, int j, int &mn, int &mx)
+{   // raw edge j of the triangle list: (0,1), (1,2), (0,2) of triangle j / 3 (ng_mesh_simplify.cpp:127-133)
+    const int t = j / 3, k = j - t * 3;
+    const int a = tri[t * 3 + (k == 2 ? 0 : k)], b = tri[t * 3 + (k == 0 ? 1 : 2)];
+    mn = min(a, b); mx = max(a, b);
+}
 
+__global__ void __launch_bounds__(SIMP_BLOCK)
+k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex *V, int *T, int4 *__restrict__ results)
+{
+    __shared__ int s_warp[SIMP_WARPS], s_any, s_last, s_bad;
+    unsigned int *s_mask = s_dyn;
+    int *s_pref = reinterpret_cast<int *>(s_dyn + ws.maskWords);
+    const SimpJobDev job = jobs[blockIdx.x];
+    const lvn_simplify_options opt = job.opt;
+    const int tid = threadIdx.x, NV = job.numVertices, NT0 = job.numTriangles;
+    lvn_mesh_vertex *meshV = V + job.vertexOffset;
+    int *tri[2] = {T + (size_t)job.triangleOffset * 3, ws.tri1 + job.edgeOff};
+
+    if (job.skip || NT0 < 100 || NV < 100) {   // ng_mesh_simplify.cpp:446-449: too small, returned untouched
+        if (tid == 0) results[job.result] = make_int4(NV, NT0, job.skip ? -2 : 0, 0);
+        return;
+    }
     // an index outside the mesh's vertices would be a wild write below (the reference would crash):
-    // such a mesh is passed through untouched and reported with iterations = -1
-    if (tid == 0) s_bad = 0;
+    // such a mesh is left untouched and reported with iterations = -1.  The same for a mesh whose
+    // ballot masks do not fit the shared memory of this launch (iterations = -2; host-side check).
+    const int NE0 = NT0 * 3;
+    if (tid == 0) { s_bad = 0; s_last = -1; }
     __syncthreads();
-    for (int i = tid; i < NT0 * 3; i += SIMP_BLOCK) if ((unsigned int)srcT[i] >= (unsigned int)NV) s_bad = 1;
+    for (int i = tid; i < NE0; i += SIMP_BLOCK) if ((unsigned int)tri[0][i] >= (unsigned int)NV) s_bad = 1;
     __syncthreads();
-    const bool bad = s_bad != 0;
-    if (bad || NT0 < 100 || NV < 100) {   // ng_mesh_simplify.cpp:446-449: too small, returned untouched
-        for (int i = tid; i < NV * 3; i += SIMP_BLOCK) reinterpret_cast<float4 *>(dstV)[i] = reinterpret_cast<const float4 *>(srcV)[i];
-        for (int i = tid; i < NT0 * 3; i += SIMP_BLOCK) dstT[i] = srcT[i];
-        if (tid == 0) results[blockIdx.x] = make_int4(NV, NT0, bad ? -1 : 0, 0);
+    if (s_bad) {
+        if (tid == 0) results[job.result] = make_int4(NV, NT0, -1, 0);
         return;
     }
     float4 *vx = ws.vx + job.vtxOff, *vn = ws.vn + job.vtxOff, *vc = ws.vc + job.vtxOff;
-    int *tri[2] = {ws.tri[0] + job.edgeOff, ws.tri[1] + job.edgeOff};   // 3 ints per triangle: same capacity as edges
     uint2 *edge[2] = {ws.edge[0] + job.edgeOff, ws.edge[1] + job.edgeOff};
-    unsigned int *bucket = ws.bucket + job.edgeOff;
-    int *eflag = ws.eflag + job.edgeOff, *escan = ws.escan + job.edgeOff;
     int *vcount = ws.vcount + job.vtxOff, *vstart = ws.vstart + job.vtxOff, *vfill = ws.vfill + job.vtxOff;
-    int *boundary = ws.boundary + job.vtxOff, *target = ws.target + job.vtxOff, *vflag = ws.vflag + job.vtxOff, *vscan = ws.vscan + job.vtxOff;
+    int *boundary = ws.boundary + job.vtxOff, *target = ws.target + job.vtxOff, *vscan = ws.vscan + job.vtxOff;
     unsigned long long *best = ws.best + job.vtxOff;
     const float4 off = make_float4(job.offset[0], job.offset[1], job.offset[2], job.offset[3]);
 
-    // ---- copy in; v.xyz -= worldSpaceOffset; per-vertex triangle counts ----
+    // ---- copy in; v.xyz -= worldSpaceOffset (ng_mesh_simplify.cpp:451-463) ----
     for (int i = tid; i < NV; i += SIMP_BLOCK) {
-        const float4 *p = reinterpret_cast<const float4 *>(&srcV[i]);
+        const float4 *p = reinterpret_cast<const float4 *>(&meshV[i]);
         const float4 x = p[0];
         vx[i] = make_float4(x.x - off.x, x.y - off.y, x.z - off.z, x.w - off.w);
         vn[i] = p[1];
         vc[i] = p[2];
-        vcount[i] = 0; vfill[i] = 0; boundary[i] = 0; vflag[i] = 0;
+        vcount[i] = 0; vfill[i] = 0; boundary[i] = 0;
     }
-    for (int i = tid; i < NT0 * 3; i += SIMP_BLOCK) tri[0][i] = srcT[i];
     __syncthreads();
 
     // ---- BuildCandidateEdges (ng_mesh_simplify.cpp:122-177) ----
-    // raw edge j of triangle t: (0,1), (1,2), (0,2); bucket by max vertex
-    const int NE0 = NT0 * 3;
+    // counting sort of the raw edges by max vertex ...
     for (int j = tid; j < NE0; j += SIMP_BLOCK) {
-        const int t = j / 3, k = j - t * 3;
-        const int a = tri[0][t * 3 + (k == 2 ? 0 : k)], b = tri[0][t * 3 + (k == 0 ? 1 : 2)];
-        atomicAdd(&vcount[max(a, b)], 1);
+        int mn, mx;
+        raw_edge(tri[0], j, mn, mx);
+        atomicAdd(&vcount[mx], 1);
+        atomicMax(&s_last, mx);     // the greatest max vertex: owner of the list's last run
     }
     __syncthreads();
-    block_scan(vcount, vstart, NV, s_warp, &s_run);
+    block_scan(vcount, vstart, NV, s_warp);
     for (int j = tid; j < NE0; j += SIMP_BLOCK) {
-        const int t = j / 3, k = j - t * 3;
-        const int a = tri[0][t * 3 + (k == 2 ? 0 : k)], b = tri[0][t * 3 + (k == 0 ? 1 : 2)];
-        const int mx = max(a, b), mn = min(a, b);
-        bucket[vstart[mx] + atomicAdd(&vfill[mx], 1)] = (unsigned int)mn;
+        int mn, mx;
+        raw_edge(tri[0], j, mn, mx);
+        edge[1][vstart[mx] + atomicAdd(&vfill[mx], 1)] = make_uint2((unsigned int)mn, (unsigned int)mx);
     }
-    if (tid == 0) { s_last[0] = -1; s_last[1] = -1; }
     __syncthreads();
-    // the greatest edge of the sorted list: greatest max vertex with a non-empty bucket, its greatest min
-    for (int v = tid; v < NV; v += SIMP_BLOCK) if (vcount[v] > 0) atomicMax(&s_last[0], v);
-    __syncthreads();
-    // each vertex sorts its bucket by min, counts runs: run of 1 -> boundary marks, longer -> one filtered edge
-    for (int v = tid; v < NV; v += SIMP_BLOCK) {
-        const int n = vcount[v], st = vstart[v];
-        for (int i = 1; i < n; i++) {   // insertion sort (a vertex has a dozen raw edges)
-            const unsigned int key = bucket[st + i];
-            int j = i - 1;
-            while (j >= 0 && bucket[st + j] > key) { bucket[st + j + 1] = bucket[st + j]; j--; }
-            bucket[st + j + 1] = key;
+    // ... then a rank sort by min inside each bucket (equal keys are interchangeable): edge[0] = std::sort's order
+#pragma unroll 2
+    for (int p = tid; p < NE0; p += SIMP_BLOCK) {
+        const uint2 e = edge[1][p];
+        const int st = vstart[e.y], n = vcount[e.y];
+        int rank = 0;
+        for (int q = 0; q < n; q++) {
+            const unsigned int k = edge[1][st + q].x;
+            rank += (k < e.x) || (k == e.x && st + q < p);
         }
-        int kept = 0;
-        for (int i = 0; i < n;) {
-            int j = i + 1;
-            while (j < n && bucket[st + j] == bucket[st + i]) j++;
-            const bool lastRun = (v == s_last[0]) && (j == n);   // never flushed by the reference's scan
-            if (!lastRun) {
-                if (j - i == 1) { boundary[bucket[st + i]] = 1; boundary[v] = 1; }
-                else bucket[st + kept++] = bucket[st + i];
-            }
-            i = j;
-        }
-        vfill[v] = kept;   // filtered edges of this bucket, ascending min, at bucket[st .. st + kept)
+        edge[0][st + rank] = e;
     }
     __syncthreads();
-    block_scan(vfill, vscan, NV, s_warp, &s_run);
+    // runs of equal edges: a run of one marks both ends as boundary, a longer run is one filtered edge;
+    // the last run of the list is never flushed by the reference's scan
+    const int lastV = s_last;
+    const unsigned int lastKey = edge[0][NE0 - 1].x;
+    ballot_pass(NE0, s_mask, [&](int p) {
+        const uint2 e = edge[0][p];
+        const bool start = p == 0 || edge[0][p - 1].x != e.x || edge[0][p - 1].y != e.y;
+        const bool more = p + 1 < NE0 && edge[0][p + 1].x == e.x && edge[0][p + 1].y == e.y;
+        const bool lastRun = (int)e.y == lastV && e.x == lastKey;
+        if (start && !more && !lastRun) { boundary[e.x] = 1; boundary[e.y] = 1; }
+        return start && more && !lastRun;
+    });
     __syncthreads();
-    const int numFiltered = s_run;
-    for (int v = tid; v < NV; v += SIMP_BLOCK) {
-        const int st = vstart[v], o = vscan[v];
-        for (int i = 0; i < vfill[v]; i++) edge[1][o + i] = make_uint2(bucket[st + i], (unsigned int)v);
+    const int numFiltered = words_prefix(s_mask, s_pref, (NE0 + 31) >> 5, s_warp);
+    for (int p = tid; p < NE0; p += SIMP_BLOCK) {
+        const int o = compact_slot(s_mask, s_pref, p);
+        if (o >= 0) edge[1][o] = edge[0][p];
     }
     __syncthreads();
-    for (int i = tid; i < numFiltered; i += SIMP_BLOCK) { const uint2 e = edge[1][i]; eflag[i] = !boundary[e.x] && !boundary[e.y]; }
+    ballot_pass(numFiltered, s_mask, [&](int i) { const uint2 e = edge[1][i]; return !boundary[e.x] && !boundary[e.y]; });
     __syncthreads();
-    block_scan(eflag, escan, numFiltered, s_warp, &s_run);
-    __syncthreads();
-    int NE = s_run;
-    for (int i = tid; i < numFiltered; i += SIMP_BLOCK) if (eflag[i]) edge[0][escan[i]] = edge[1][i];
+    int NE = words_prefix(s_mask, s_pref, (numFiltered + 31) >> 5, s_warp);
+    for (int i = tid; i < numFiltered; i += SIMP_BLOCK) {
+        const int o = compact_slot(s_mask, s_pref, i);
+        if (o >= 0) edge[0][o] = edge[1][i];
+    }
     // vertexTriangleCounts (ng_mesh_simplify.cpp:478-489)
     for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
     __syncthreads();
-    for (int i = tid; i < NT0 * 3; i += SIMP_BLOCK) atomicAdd(&vcount[tri[0][i]], 1);
+    for (int i = tid; i < NE0; i += SIMP_BLOCK) atomicAdd(&vcount[tri[0][i]], 1);
     __syncthreads();
 
     int NT = NT0, curT = 0, curE = 0;
@@ -372,36 +429,32 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws,
     int iterations = 0;
     while (NT > targetTriangleCount && iterations++ < opt.maxIterations) {
         for (int i = tid; i < NV; i += SIMP_BLOCK) { best[i] = ~0ull; target[i] = -1; }
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
+        if (tid == 0) s_any = 0;
         // ---- FindValidCollapses (ng_mesh_simplify.cpp:181-283) ----
         const int numRandom = (int)((float)NE * opt.edgeFraction);
         if (numRandom > 0) {
             // std::uniform_int_distribution<int>(0, NE - 1) over std::mt19937(42), libstdc++:
             // product = raw * range; reject while (uint32)product < (2^32 - range) % range
             const unsigned int range = (unsigned int)NE, threshold = (0u - range) % range;
-            const int K = min(numRandom + 256, SIMP_RAW);
-            for (int base = 0; base < K; base += SIMP_BLOCK) {
-                const int k = base + tid;
-                if (k < K) {
-                    const unsigned long long prod = (unsigned long long)ws.raw[k] * range;
-                    eflag[k] = ((unsigned int)prod >= threshold) ? 1 : 0;   // accepted draw
-                }
-            }
+            const int K = numRandom + SIMP_SLACK;
+            ballot_pass(K, s_mask, [&](int k) { return (unsigned int)((unsigned long long)ws.raw[k] * range) >= threshold; });
             __syncthreads();
-            block_scan(eflag, escan, K, s_warp, &s_run);
-            __syncthreads();
+            words_prefix(s_mask, s_pref, (K + 31) >> 5, s_warp);
+            const uint2 *edges = edge[curE];
+#pragma unroll 2
             for (int k = tid; k < K; k += SIMP_BLOCK) {
-                if (!eflag[k] || escan[k] >= numRandom) continue;
+                const int rank = compact_slot(s_mask, s_pref, k);       // this draw's place among the accepted ones
+                if (rank < 0 || rank >= numRandom) continue;
                 const int i = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
-                const uint2 e = edge[curE][i];
+                const uint2 e = edges[i];
                 const float4 nMin = vn[e.x], nMax = vn[e.y];
-                if (dot4_lr(nMin, nMax) < opt.minAngleCosine) continue;
                 const float4 pMin = vx[e.x], pMax = vx[e.y];
+                const float mMin = vc[e.x].w, mMax = vc[e.y].w;
+                const int degree = vcount[e.x] + vcount[e.y];
+                if (dot4_lr(nMin, nMax) < opt.minAngleCosine) continue;
                 const float4 d = make_float4(pMax.x - pMin.x, pMax.y - pMin.y, pMax.z - pMin.z, pMax.w - pMin.w);
                 if (dot4_lr(d, d) > maxEdge2) continue;
-                if ((double)fabsf(vc[e.x].w - vc[e.y].w) > 1e-3) continue;
-                const int degree = vcount[e.x] + vcount[e.y];
+                if ((double)fabsf(mMin - mMax) > 1e-3) continue;
                 if (degree > SIMP_MAX_DEGREE) continue;
                 float pos[4];
                 float error = qef4_solve2(pMin, nMin, pMax, nMax, pos);
@@ -412,11 +465,11 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws,
                 const unsigned long long pack = ((unsigned long long)__float_as_uint(error) << 32) | (unsigned int)i;
                 atomicMin(&best[e.x], pack);
                 atomicMin(&best[e.y], pack);
-                atomicAdd(&s_cnt, 1);
+                s_any = 1;
             }
         }
         __syncthreads();
-        if (s_cnt == 0) break;
+        if (s_any == 0) break;
         // ---- CollapseEdges (ng_mesh_simplify.cpp:287-311): one thread per min vertex ----
         for (int v = tid; v < NV; v += SIMP_BLOCK) {
             const unsigned long long b = best[v];
@@ -434,79 +487,230 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws,
             vn[e.x] = make_float4((nMin.x - nMax.x) * 0.5f, (nMin.y - nMax.y) * 0.5f, (nMin.z - nMax.z) * 0.5f, (nMin.w - nMax.w) * 0.5f);
         }
         __syncthreads();
-        // ---- RemoveTriangles (ng_mesh_simplify.cpp:315-360) ----
+        // ---- RemoveTriangles (ng_mesh_simplify.cpp:315-360) and RemoveEdges (:364-391) ----
+        // triangles first (their masks leave shared memory before the edges' masks enter)
         for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
-        for (int t = tid; t < NT; t += SIMP_BLOCK) {
-            int a = tri[curT][t * 3], b = tri[curT][t * 3 + 1], c = tri[curT][t * 3 + 2];
-            const int ta = target[a], tb = target[b], tc = target[c];
-            if (ta != -1) a = ta;
-            if (tb != -1) b = tb;
-            if (tc != -1) c = tc;
-            tri[curT][t * 3] = a; tri[curT][t * 3 + 1] = b; tri[curT][t * 3 + 2] = c;
-            eflag[t] = !(a == b || a == c || b == c);
-        }
-        __syncthreads();
-        block_scan(eflag, escan, NT, s_warp, &s_run);
-        __syncthreads();
-        const int newNT = s_run;
-        for (int t = tid; t < NT; t += SIMP_BLOCK) {
-            if (!eflag[t]) continue;
-            const int o = escan[t] * 3;
+        {
+            const int *src = tri[curT];
+            ballot_pass(NT, s_mask, [&](int t) {
+                int a = src[t * 3], b = src[t * 3 + 1], c = src[t * 3 + 2];
+                const int ta = target[a], tb = target[b], tc = target[c];
+                if (ta != -1) a = ta;
+                if (tb != -1) b = tb;
+                if (tc != -1) c = tc;
+                return !(a == b || a == c || b == c);
+            });
+            __syncthreads();
+            const int newNT = words_prefix(s_mask, s_pref, (NT + 31) >> 5, s_warp);
+            int *dst = tri[curT ^ 1];
+#pragma unroll 2
+            for (int t = tid; t < NT; t += SIMP_BLOCK) {
+                const int o = compact_slot(s_mask, s_pref, t);
+                if (o < 0) continue;
 #pragma unroll
-            for (int k = 0; k < 3; k++) { const int idx = tri[curT][t * 3 + k]; tri[curT ^ 1][o + k] = idx; atomicAdd(&vcount[idx], 1); }
+                for (int k = 0; k < 3; k++) {
+                    int idx = src[t * 3 + k];
+                    const int tg = target[idx];
+                    if (tg != -1) idx = tg;
+                    dst[o * 3 + k] = idx;
+                    atomicAdd(&vcount[idx], 1);
+                }
+            }
+            __syncthreads();
+            NT = newNT; curT ^= 1;
         }
-        __syncthreads();
-        NT = newNT; curT ^= 1;
-        // ---- RemoveEdges (ng_mesh_simplify.cpp:364-391) ----
-        for (int i = tid; i < NE; i += SIMP_BLOCK) {
-            uint2 e = edge[curE][i];
-            const int t0 = target[e.x], t1 = target[e.y];
-            if (t0 != -1) e.x = (unsigned int)t0;
-            if (t1 != -1) e.y = (unsigned int)t1;
-            edge[curE][i] = e;
-            eflag[i] = e.x != e.y;
+        {
+            const uint2 *src = edge[curE];
+            ballot_pass(NE, s_mask, [&](int i) {
+                uint2 e = src[i];
+                const int t0 = target[e.x], t1 = target[e.y];
+                if (t0 != -1) e.x = (unsigned int)t0;
+                if (t1 != -1) e.y = (unsigned int)t1;
+                return e.x != e.y;
+            });
+            __syncthreads();
+            const int newNE = words_prefix(s_mask, s_pref, (NE + 31) >> 5, s_warp);
+            uint2 *dst = edge[curE ^ 1];
+#pragma unroll 2
+            for (int i = tid; i < NE; i += SIMP_BLOCK) {
+                const int o = compact_slot(s_mask, s_pref, i);
+                if (o < 0) continue;
+                uint2 e = src[i];
+                const int t0 = target[e.x], t1 = target[e.y];
+                if (t0 != -1) e.x = (unsigned int)t0;
+                if (t1 != -1) e.y = (unsigned int)t1;
+                dst[o] = e;
+            }
+            __syncthreads();
+            NE = newNE; curE ^= 1;
         }
-        __syncthreads();
-        block_scan(eflag, escan, NE, s_warp, &s_run);
-        __syncthreads();
-        const int newNE = s_run;
-        for (int i = tid; i < NE; i += SIMP_BLOCK) if (eflag[i]) edge[curE ^ 1][escan[i]] = edge[curE][i];
-        __syncthreads();
-        NE = newNE; curE ^= 1;
     }
     __syncthreads();
 
     // ---- CompactVertices + write back (ng_mesh_simplify.cpp:395-437,520-539) ----
-    for (int i = tid; i < NV; i += SIMP_BLOCK) vflag[i] = 0;
+    for (int i = tid; i < NV; i += SIMP_BLOCK) vfill[i] = 0;
     __syncthreads();
-    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) vflag[tri[curT][i]] = 1;
+    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) vfill[tri[curT][i]] = 1;
     __syncthreads();
-    block_scan(vflag, vscan, NV, s_warp, &s_run);
-    __syncthreads();
-    const int newNV = s_run;
+    const int newNV = block_scan(vfill, vscan, NV, s_warp);
     for (int i = tid; i < NV; i += SIMP_BLOCK) {
-        if (!vflag[i]) continue;
-        float4 *p = reinterpret_cast<float4 *>(&dstV[vscan[i]]);
+        if (!vfill[i]) continue;
+        float4 *p = reinterpret_cast<float4 *>(&meshV[vscan[i]]);
         const float4 x = vx[i];
         p[0] = make_float4(x.x + off.x, x.y + off.y, x.z + off.z, x.w + off.w);
         p[1] = vn[i];
         p[2] = vc[i];
     }
-    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) dstT[i] = vscan[tri[curT][i]];
-    if (tid == 0) results[blockIdx.x] = make_int4(newNV, NT, iterations, NE);
+    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) tri[0][i] = vscan[tri[curT][i]];   // each element read and written by one thread
+    if (tid == 0) results[job.result] = make_int4(newNV, NT, iterations, NE);
+}
+
+// The simplified meshes, left at the start of their slices, gathered into dense arrays in mesh
+// order: one block per mesh; a mesh's place = the counts of the meshes before it.
+__global__ void __launch_bounds__(256)
+k_pack_meshes(const SimpJobDev *__restrict__ jobsByMesh, const int4 *__restrict__ results, int numMeshes,
+              const lvn_mesh_vertex *__restrict__ V, const int *__restrict__ T,
+              lvn_mesh_vertex *__restrict__ outV, int *__restrict__ outT, int2 *__restrict__ packedOffsets, int2 *__restrict__ totals)
+{
+    __shared__ int s_v[8], s_t[8];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    int sv = 0, st = 0;
+    for (int i = tid; i < m; i += 256) { const int4 r = results[i]; sv += r.x; st += r.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); st += __shfl_xor_sync(0xffffffffu, st, o); }
+    if ((tid & 31) == 0) { s_v[tid >> 5] = sv; s_t[tid >> 5] = st; }
+    __syncthreads();
+    int baseV = 0, baseT = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { baseV += s_v[q]; baseT += s_t[q]; }
+    const SimpJobDev job = jobsByMesh[m];
+    const int4 r = results[m];
+    const float4 *src = reinterpret_cast<const float4 *>(V + job.vertexOffset);
+    float4 *dst = reinterpret_cast<float4 *>(outV + baseV);
+    for (int i = tid; i < r.x * 3; i += 256) dst[i] = src[i];
+    const int *ts = T + (size_t)job.triangleOffset * 3;
+    int *td = outT + (size_t)baseT * 3;
+    for (int i = tid; i < r.y * 3; i += 256) td[i] = ts[i];
+    if (tid == 0) {
+        packedOffsets[m] = make_int2(baseV, baseT);
+        if (m == numMeshes - 1) *totals = make_int2(baseV + r.x, baseT + r.y);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 struct SimpState {
     cudaStream_t stream = nullptr;
-    void *d_blob = nullptr; size_t blobCap = 0;
-    unsigned int *d_raw = nullptr;
+    void *d_blob = nullptr; size_t blobCap = 0;       // scratch of a launch
+    void *d_io = nullptr; size_t ioCap = 0;           // host path: the caller's arrays on the device
+    unsigned int *d_raw = nullptr; int rawCount = 0;
+    size_t smemSet = 0;
 };
 static SimpState g_simp;
 static const char *g_simpError = "";
 static int simp_fail(cudaError_t e) { g_simpError = cudaGetErrorString(e); cudaGetLastError(); return LVN_ERR_CUDA; }
+#define LV(call) do { int r_ = (call); if (r_ < 0) return r_; } while (0)
 #define MCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return simp_fail(e_); } while (0)
 static size_t simp_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+const char *simplify_last_error() { return g_simpError; }
+
+// the raw stream of std::mt19937 seeded with 42 (ng_mesh_simplify.cpp:195-196); the engine is standardised
+static int ensure_raw(int count)
+{
+    if (count <= g_simp.rawCount) return LVN_SUCCESS;
+    int cap = 1 << 16;
+    while (cap < count) cap <<= 1;
+    std::vector<unsigned int> raw(cap);
+    std::mt19937 prng;
+    prng.seed(42);
+    for (int i = 0; i < cap; i++) raw[i] = (unsigned int)prng();
+    if (g_simp.d_raw) { MCU(cudaDeviceSynchronize()); MCU(cudaFree(g_simp.d_raw)); g_simp.d_raw = nullptr; g_simp.rawCount = 0; }
+    MCU(cudaMalloc(&g_simp.d_raw, sizeof(unsigned int) * cap));
+    MCU(cudaMemcpy(g_simp.d_raw, raw.data(), sizeof(unsigned int) * cap, cudaMemcpyHostToDevice));
+    g_simp.rawCount = cap;
+    return LVN_SUCCESS;
+}
+
+static int ensure_buffer(void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return LVN_SUCCESS;
+    if (*p) { MCU(cudaDeviceSynchronize()); MCU(cudaFree(*p)); *p = nullptr; *cap = 0; }
+    MCU(cudaMalloc(p, bytes + bytes / 4));
+    *cap = bytes + bytes / 4;
+    return LVN_SUCCESS;
+}
+
+// Simplify n meshes in place in their slices of d_V / d_T, asynchronously on `st`.
+// d_results[m] (device, mesh order) = (vertices, triangles, iterations, candidate edges left).
+// With d_packV / d_packT the simplified meshes are also gathered densely, in mesh order:
+// d_packOffsets[m] = (first vertex, first triangle), *d_packTotals = the totals.
+int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int *d_T, int4 *d_results,
+                    lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st)
+{
+    if (n <= 0) return LVN_SUCCESS;
+    std::vector<SimpJobDev> jd(n);
+    long long edgeTotal = 0, vtxTotal = 0;
+    int maxElems = 0, maxDraws = 0;
+    for (int m = 0; m < n; m++) {
+        const SimplifyMesh &j = meshes[m];
+        SimpJobDev &d = jd[m];
+        if (!(j.opt.edgeFraction >= 0.f)) return LVN_ERR_INVALID_VALUE;
+        d.vertexOffset = j.vertexOffset; d.numVertices = j.numVertices;
+        d.triangleOffset = j.triangleOffset; d.numTriangles = j.numTriangles;
+        memcpy(d.offset, j.offset, sizeof(d.offset));
+        d.opt = j.opt;
+        d.edgeOff = edgeTotal; d.vtxOff = (int)vtxTotal; d.result = m; d.skip = 0;
+        if (j.numTriangles < 100 || j.numVertices < 100) continue;    // passes through: no scratch
+        const double draws = (double)j.numTriangles * 3.0 * (double)j.opt.edgeFraction + SIMP_SLACK;
+        const double elems = std::max((double)j.numTriangles * 3.0, draws);
+        if (elems / 32.0 * 8.0 + 64 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // reported as iterations = -2
+        maxElems = std::max(maxElems, (int)elems);
+        maxDraws = std::max(maxDraws, (int)draws);
+        edgeTotal += ((long long)j.numTriangles * 3 + 3) & ~3ll;
+        vtxTotal += (j.numVertices + 3) & ~3;
+        if (vtxTotal > 0x7fffffffll) return LVN_ERR_CAPACITY;
+    }
+    LV(ensure_raw(maxDraws));
+    const int maskWords = ((maxElems + 31) / 32 + 31) & ~31;
+    const size_t smem = (size_t)maskWords * 8;
+    if (smem > 48 * 1024 && smem > g_simp.smemSet) {
+        MCU(cudaFuncSetAttribute(k_simplify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMP_MAX_SMEM));
+        g_simp.smemSet = SIMP_MAX_SMEM;
+    }
+    // launch order: largest meshes first (a block per mesh; the tail of the launch is small meshes)
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jd[a].numTriangles > jd[b].numTriangles; });
+    std::vector<SimpJobDev> launch(n);
+    for (int i = 0; i < n; i++) launch[i] = jd[order[i]];
+
+    const size_t E = (size_t)std::max<long long>(edgeTotal, 4), NVt = (size_t)std::max<long long>(vtxTotal, 4);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += simp_align(bytes); return o; };
+    const size_t oLaunch = take(sizeof(SimpJobDev) * n), oJobs = take(sizeof(SimpJobDev) * n),
+                 oVx = take(16 * NVt), oVn = take(16 * NVt), oVc = take(16 * NVt), oT1 = take(4 * E),
+                 oE0 = take(8 * E), oE1 = take(8 * E), oVcnt = take(4 * NVt), oVst = take(4 * NVt), oVfl = take(4 * NVt),
+                 oBd = take(4 * NVt), oTg = take(4 * NVt), oVs = take(4 * NVt), oBest = take(8 * NVt);
+    LV(ensure_buffer(&g_simp.d_blob, &g_simp.blobCap, off));
+    char *B = (char *)g_simp.d_blob;
+    MCU(cudaMemcpyAsync(B + oLaunch, launch.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
+    SimpScratch ws;
+    ws.vx = (float4 *)(B + oVx); ws.vn = (float4 *)(B + oVn); ws.vc = (float4 *)(B + oVc);
+    ws.tri1 = (int *)(B + oT1);
+    ws.edge[0] = (uint2 *)(B + oE0); ws.edge[1] = (uint2 *)(B + oE1);
+    ws.vcount = (int *)(B + oVcnt); ws.vstart = (int *)(B + oVst); ws.vfill = (int *)(B + oVfl); ws.boundary = (int *)(B + oBd);
+    ws.target = (int *)(B + oTg); ws.vscan = (int *)(B + oVs); ws.best = (unsigned long long *)(B + oBest);
+    ws.raw = g_simp.d_raw;
+    ws.maskWords = maskWords;
+    k_simplify<<<n, SIMP_BLOCK, smem, st>>>((const SimpJobDev *)(B + oLaunch), ws, d_V, d_T, d_results);
+    MCU(cudaGetLastError());
+    if (d_packV) {
+        MCU(cudaMemcpyAsync(B + oJobs, jd.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
+        k_pack_meshes<<<n, 256, 0, st>>>((const SimpJobDev *)(B + oJobs), d_results, n, d_V, d_T, d_packV, d_packT, d_packOffsets, d_packTotals);
+        MCU(cudaGetLastError());
+    }
+    return LVN_SUCCESS;
+}
 
 }  // namespace lvn
 
@@ -519,85 +723,46 @@ extern "C" int lvn_mesh_simplify_batch(int numMeshes, const lvn_simplify_job *jo
                                        lvn_mesh_triangle *triangles, int64_t numTrianglesTotal,
                                        lvn_simplify_result *results)
 {
-    if (numMeshes < 0 || !options || (numOptions != 1 && numOptions != numMeshes) || (numMeshes > 0 && (!jobs || !results || !vertices || !triangles))) return LVN_ERR_INVALID_VALUE;
+    if (numMeshes < 0 || !options || (numOptions != 1 && numOptions != numMeshes) ||
+        (numMeshes > 0 && (!jobs || !results || !vertices || !triangles))) return LVN_ERR_INVALID_VALUE;
     if (numMeshes == 0) return LVN_SUCCESS;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return LVN_ERR_NO_DEVICE; }
     if (!g_simp.stream) MCU(cudaStreamCreateWithFlags(&g_simp.stream, cudaStreamNonBlocking));
     cudaStream_t st = g_simp.stream;
-    if (!g_simp.d_raw) {
-        // the raw stream of std::mt19937 seeded with 42 (ng_mesh_simplify.cpp:195-196); the engine is standardised
-        std::vector<unsigned int> raw(SIMP_RAW);
-        std::mt19937 prng;
-        prng.seed(42);
-        for (int i = 0; i < SIMP_RAW; i++) raw[i] = (unsigned int)prng();
-        MCU(cudaMalloc(&g_simp.d_raw, sizeof(unsigned int) * SIMP_RAW));
-        MCU(cudaMemcpy(g_simp.d_raw, raw.data(), sizeof(unsigned int) * SIMP_RAW, cudaMemcpyHostToDevice));
-    }
-    std::vector<SimpJobDev> jd(numMeshes);
-    long long edgeTotal = 0;
-    long long vtxTotal = 0;
+    std::vector<SimplifyMesh> meshes(numMeshes);
     for (int m = 0; m < numMeshes; m++) {
         const lvn_simplify_job &j = jobs[m];
         if (j.numVertices < 0 || j.numTriangles < 0 || j.vertexOffset < 0 || j.triangleOffset < 0 ||
             (int64_t)j.vertexOffset + j.numVertices > numVerticesTotal || (int64_t)j.triangleOffset + j.numTriangles > numTrianglesTotal)
             return LVN_ERR_INVALID_VALUE;
-        // the candidate sample of one iteration must fit the precomputed raw stream
-        const lvn_simplify_options &o = options[numOptions == 1 ? 0 : m];
-        if (!(o.edgeFraction >= 0.f)) return LVN_ERR_INVALID_VALUE;
-        if ((int64_t)j.numTriangles * 3 * (double)o.edgeFraction + 256 > SIMP_RAW) return LVN_ERR_CAPACITY;
-        SimpJobDev &d = jd[m];
-        d.opt = SimpOptionsDev{o.edgeFraction, o.maxIterations, o.targetPercentage, o.maxError, o.maxEdgeSize, o.minAngleCosine};
+        SimplifyMesh &d = meshes[m];
         d.vertexOffset = j.vertexOffset; d.numVertices = j.numVertices;
         d.triangleOffset = j.triangleOffset; d.numTriangles = j.numTriangles;
         memcpy(d.offset, j.worldSpaceOffset, sizeof(d.offset));
-        d.edgeOff = edgeTotal; d.vtxOff = (int)vtxTotal;
-        // eflag / escan also hold the sampler's flags: numRandom + 256 draws of one iteration
-        edgeTotal += (long long)((double)j.numTriangles * 3 * std::max(1.0, (double)o.edgeFraction)) + 256;
-        vtxTotal += j.numVertices;
+        d.opt = options[numOptions == 1 ? 0 : m];
     }
-    const size_t E = (size_t)std::max<long long>(edgeTotal, 1), V = (size_t)std::max<long long>(vtxTotal, 1);
-    size_t off = 0;
-    auto take = [&](size_t bytes) { const size_t o = off; off += simp_align(bytes); return o; };
-    const size_t oJobs = take(sizeof(SimpJobDev) * numMeshes), oInV = take(sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal),
-                 oInT = take(12 * (size_t)numTrianglesTotal), oOutV = take(sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal),
-                 oOutT = take(12 * (size_t)numTrianglesTotal), oRes = take(sizeof(int4) * numMeshes),
-                 oVx = take(16 * V), oVn = take(16 * V), oVc = take(16 * V), oT0 = take(4 * E), oT1 = take(4 * E),
-                 oE0 = take(8 * E), oE1 = take(8 * E), oBk = take(4 * E), oEf = take(4 * E), oEs = take(4 * E),
-                 oVcnt = take(4 * V), oVst = take(4 * V), oVfl = take(4 * V), oBd = take(4 * V), oTg = take(4 * V), oVf = take(4 * V),
-                 oVs = take(4 * V), oBest = take(8 * V);
-    if (off > g_simp.blobCap) {
-        if (g_simp.d_blob) MCU(cudaFree(g_simp.d_blob));
-        g_simp.d_blob = nullptr; g_simp.blobCap = 0;
-        MCU(cudaMalloc(&g_simp.d_blob, off + off / 4));
-        g_simp.blobCap = off + off / 4;
-    }
-    char *B = (char *)g_simp.d_blob;
-    MCU(cudaMemcpyAsync(B + oJobs, jd.data(), sizeof(SimpJobDev) * numMeshes, cudaMemcpyHostToDevice, st));
-    MCU(cudaMemcpyAsync(B + oInV, vertices, sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal, cudaMemcpyHostToDevice, st));
-    MCU(cudaMemcpyAsync(B + oInT, triangles, 12 * (size_t)numTrianglesTotal, cudaMemcpyHostToDevice, st));
-    SimpScratch ws;
-    ws.vx = (float4 *)(B + oVx); ws.vn = (float4 *)(B + oVn); ws.vc = (float4 *)(B + oVc);
-    ws.tri[0] = (int *)(B + oT0); ws.tri[1] = (int *)(B + oT1);
-    ws.edge[0] = (uint2 *)(B + oE0); ws.edge[1] = (uint2 *)(B + oE1);
-    ws.bucket = (unsigned int *)(B + oBk); ws.eflag = (int *)(B + oEf); ws.escan = (int *)(B + oEs);
-    ws.vcount = (int *)(B + oVcnt); ws.vstart = (int *)(B + oVst); ws.vfill = (int *)(B + oVfl); ws.boundary = (int *)(B + oBd);
-    ws.target = (int *)(B + oTg); ws.vflag = (int *)(B + oVf); ws.vscan = (int *)(B + oVs); ws.best = (unsigned long long *)(B + oBest);
-    ws.raw = g_simp.d_raw;
-    k_simplify<<<numMeshes, SIMP_BLOCK, 0, st>>>((const SimpJobDev *)(B + oJobs), ws, (const lvn_mesh_vertex *)(B + oInV),
-                                                 (const int *)(B + oInT), (lvn_mesh_vertex *)(B + oOutV), (int *)(B + oOutT), (int4 *)(B + oRes));
-    MCU(cudaGetLastError());
+    const size_t bV = simp_align(sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal), bT = simp_align(12 * (size_t)numTrianglesTotal);
+    LV(ensure_buffer(&g_simp.d_io, &g_simp.ioCap, bV + bT + simp_align(sizeof(int4) * numMeshes)));
+    char *IO = (char *)g_simp.d_io;
+    lvn_mesh_vertex *dV = (lvn_mesh_vertex *)IO;
+    int *dT = (int *)(IO + bV);
+    int4 *dRes = (int4 *)(IO + bV + bT);
+    MCU(cudaMemcpyAsync(dV, vertices, sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal, cudaMemcpyHostToDevice, st));
+    MCU(cudaMemcpyAsync(dT, triangles, 12 * (size_t)numTrianglesTotal, cudaMemcpyHostToDevice, st));
+    LV(simplify_device(numMeshes, meshes.data(), dV, dT, dRes, nullptr, nullptr, nullptr, nullptr, st));
     std::vector<int4> res(numMeshes);
-    MCU(cudaMemcpyAsync(res.data(), B + oRes, sizeof(int4) * numMeshes, cudaMemcpyDeviceToHost, st));
+    MCU(cudaMemcpyAsync(res.data(), dRes, sizeof(int4) * numMeshes, cudaMemcpyDeviceToHost, st));
     // the simplified meshes stay in their input slots (a mesh never grows): two copies back
-    MCU(cudaMemcpyAsync(vertices, B + oOutV, sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal, cudaMemcpyDeviceToHost, st));
-    MCU(cudaMemcpyAsync(triangles, B + oOutT, 12 * (size_t)numTrianglesTotal, cudaMemcpyDeviceToHost, st));
+    MCU(cudaMemcpyAsync(vertices, dV, sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal, cudaMemcpyDeviceToHost, st));
+    MCU(cudaMemcpyAsync(triangles, dT, 12 * (size_t)numTrianglesTotal, cudaMemcpyDeviceToHost, st));
     MCU(cudaStreamSynchronize(st));
     int rc = LVN_SUCCESS;
     for (int m = 0; m < numMeshes; m++) {
         results[m].numVertices = res[m].x; results[m].numTriangles = res[m].y;
         results[m].iterations = res[m].z; results[m].numEdges = res[m].w;
-        if (res[m].z < 0) { rc = LVN_ERR_INVALID_VALUE; g_simpError = "a triangle index lies outside its mesh's vertices"; }
+        if (res[m].z == -1) { rc = LVN_ERR_INVALID_VALUE; g_simpError = "a triangle index lies outside its mesh's vertices"; }
+        else if (res[m].z == -2 && rc == LVN_SUCCESS) { rc = LVN_ERR_CAPACITY; g_simpError = "a mesh is too large for the simplifier's shared-memory masks"; }
     }
     return rc;
 }

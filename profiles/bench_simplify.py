@@ -17,8 +17,21 @@ assert lc.Compute_Initialise(B.SEED, 0, 2) == 0
 ctx = lc.Compute_MeshGenContext.create(64)
 
 
+_keep = []
+
+
+def pinned(n, dtype):
+    a = lc.PinnedArray(n, dtype)
+    _keep.append(a)
+    return a.array
+
+
+TOTALS = {}
+
+
 def chunk_meshes(ms):
     rc, res, view = ctx.generateBatchDevice(ms)
+    TOTALS.update(v=int(view.totalVertices) + 1, t=int(view.totalTriangles) + 1, s=int(view.totalSeamNodes) + 1)
     V = np.zeros(int(view.totalVertices) + 1, lc.MeshVertex); T = np.zeros(int(view.totalTriangles) + 1, lc.MeshTriangle)
     Sn = np.zeros(int(view.totalSeamNodes) + 1, lc.SeamNodeInfo)
     rc, res = ctx.generateBatch(ms, V, T, Sn)
@@ -36,8 +49,9 @@ def run(name, ms, check):
     jobs, V0, T0 = lc.PackSimplifyMeshes(meshes)
     opt = lc.SimplifyOptions.for_clipmap_node(256)
     times = []
+    V, T = pinned(len(V0), lc.MeshVertex), pinned(len(T0), lc.MeshTriangle)     # the caller's arrays: pinned, as MeshBuffer pools would be
     for it in range(8):
-        V, T = V0.copy(), T0.copy()
+        V[:] = V0; T[:] = T0
         t0 = time.perf_counter()
         rc, res = lc.ngMeshSimplifierPacked(jobs, opt, V, T)
         times.append(time.perf_counter() - t0)
@@ -47,7 +61,24 @@ def run(name, ms, check):
            "triangles_in": int(jobs["numTriangles"].sum()), "vertices_out": int(res["numVertices"].sum()),
            "triangles_out": int(res["numTriangles"].sum()), "iterations_mean": float(res["iterations"].mean()),
            "gpu_ms_per_batch": gpu_s * 1e3, "gpu_meshes_per_s": len(meshes) / gpu_s,
-           "gpu_what": "one lvn_mesh_simplify_batch call: H2D of the meshes (pageable), one kernel (a block per mesh), D2H"}
+           "gpu_what": "one lvn_mesh_simplify_batch call: H2D of the meshes (pinned), one kernel (a block per mesh), D2H"}
+    # the fused route: generate + simplify in HBM, simplified meshes out (lvn_meshgen_generate_simplified_batch)
+    Vf, Tf, Sf = pinned(TOTALS['v'], lc.MeshVertex), pinned(TOTALS['t'], lc.MeshTriangle), pinned(TOTALS['s'], lc.SeamNodeInfo)
+    tf, tg = [], []
+    for it in range(8):
+        t0 = time.perf_counter()
+        rc, fres, fsimp = ctx.generateSimplifiedBatch(ms, Vf, Tf, Sf)
+        tf.append(time.perf_counter() - t0)
+        assert rc == 0, lc.last_cuda_error()
+        t0 = time.perf_counter()
+        rc, gres = ctx.generateBatch(ms, Vf, Tf, Sf)
+        tg.append(time.perf_counter() - t0)
+        assert rc == 0
+    out.update(fused_ms_per_batch=float(np.median(tf[2:])) * 1e3, fused_chunks_per_s=len(ms) / float(np.median(tf[2:])),
+               generate_only_ms_per_batch=float(np.median(tg[2:])) * 1e3,
+               fused_what="lvn_meshgen_generate_simplified_batch: chunk list in, simplified meshes + seam nodes out (pinned arenas)",
+               fused_vertices_out=int(fres["numVertices"].sum()), fused_triangles_out=int(fres["numTriangles"].sum()))
+    assert out["fused_vertices_out"] == out["vertices_out"] and out["fused_triangles_out"] == out["triangles_out"]
     if R.simplify_available():
         ropt = S.clipmap_options(256)
         ref_s, bad = 0.0, 0

@@ -211,3 +211,62 @@ def test_gpu_simplify_edge_cases(lc):
     jobs[0]["numVertices"] = 4
     assert c.lib().lvn_mesh_simplify_batch(1, c._ptr(jobs), o1, 2, c._ptr(V), 4, c._ptr(T), 5, c._ptr(r)) == c.LVN_ERR_INVALID_VALUE
     assert c.lib().lvn_mesh_simplify_batch(1, c._ptr(jobs), None, 1, c._ptr(V), 4, c._ptr(T), 5, c._ptr(r)) == c.LVN_ERR_INVALID_VALUE
+
+
+@pytest.mark.gpu
+def test_gpu_generate_simplified_batch(lc, world, surface_cy, golden, built):
+    """lvn_meshgen_generate_simplified_batch = ConstructClipmapNodeData over a batch (mixed LODs, empty
+    chunks among them): same meshes as generateChunkMesh followed by ngMeshSimplifier with the
+    clipmap's per-node options -- against the committed digests of the reference simplifier, against
+    the two-step GPU route, and against the reference itself where it is built"""
+    from oracle import ref as R
+    rows, _ = golden
+    named = S.chunk_cases(world, surface_cy)
+    chunks = [list(mn) + [size] for name, mn, size in named] + [[0, 15 * 256, 0, 256], [0, 0, 0, 256]]   # + air, solid
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        V = np.zeros(200000, lc.MeshVertex); T = np.zeros(400000, lc.MeshTriangle); Sn = np.zeros(100000, lc.SeamNodeInfo)
+        rc, res, simp = ctx.generateSimplifiedBatch(chunks, V, T, Sn)
+        assert rc == 0, lc.last_cuda_error()
+        V2 = np.zeros(200000, lc.MeshVertex); T2 = np.zeros(400000, lc.MeshTriangle); Sn2 = np.zeros(100000, lc.SeamNodeInfo)
+        rc, res2 = ctx.generateBatch(chunks, V2, T2, Sn2)
+        assert rc == 0
+        assert res[-1]["numVertices"] == 0 and res[-2]["numVertices"] == 0 and simp[-1]["iterations"] == 0
+        # dense packing in chunk order
+        nz = [r for r in res if r["numTriangles"]]
+        assert nz[0]["vertexOffset"] == 0 and nz[0]["triangleOffset"] == 0
+        for a, b in zip(nz, nz[1:]):
+            assert b["vertexOffset"] == a["vertexOffset"] + a["numVertices"] and b["triangleOffset"] == a["triangleOffset"] + a["numTriangles"]
+        seen = 0
+        for (name, mn, size), r, r2, sr in zip(named, res, res2, simp):
+            # seam nodes are those of the unsimplified octree
+            assert r["numSeamNodes"] == r2["numSeamNodes"] and r["numEdges"] == r2["numEdges"]
+            assert Sn[r["seamOffset"]:r["seamOffset"] + r["numSeamNodes"]].tobytes() == Sn2[r2["seamOffset"]:r2["seamOffset"] + r2["numSeamNodes"]].tobytes()
+            if r2["numTriangles"] == 0:
+                assert r["numTriangles"] == 0
+                continue
+            gv = S.as_vertices(V[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]])
+            gt = T["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]]
+            assert (str(len(gv)), str(len(gt)), sha(gv), sha(gt)) == tuple(rows[name][4:]), (name, "vs golden")
+            assert sr["numVertices"] == len(gv) and sr["numTriangles"] == len(gt) and sr["iterations"] > 0
+            v2 = V2[r2["vertexOffset"]:r2["vertexOffset"] + r2["numVertices"]]
+            t2 = T2[r2["triangleOffset"]:r2["triangleOffset"] + r2["numTriangles"]]
+            centre = [mn[0] + size / 2.0, mn[1] + size / 2.0, mn[2] + size / 2.0]
+            rc, out, _ = lc.ngMeshSimplifierBatch([(v2, t2, centre)], lc.SimplifyOptions.for_clipmap_node(size))
+            assert rc == 0 and S.as_vertices(out[0][0]).tobytes() == gv.tobytes() and np.array_equal(out[0][1]["indices_"], gt)
+            if R.simplify_available():
+                rv, rt = R.simplify_mesh(S.as_vertices(v2), t2["indices_"], centre, S.clipmap_options(size))
+                assert rv.tobytes() == gv.tobytes() and np.array_equal(rt, gt), name
+            seen += 1
+        assert seen >= 15
+        # arenas too small: LVN_ERR_CAPACITY, and the counts say what is needed
+        rc, res3, _ = ctx.generateSimplifiedBatch(chunks, V[:100], T[:100], Sn)
+        assert rc == lc.LVN_ERR_CAPACITY and np.array_equal(res3["numVertices"], res["numVertices"])
+        rc, res3, _ = ctx.generateSimplifiedBatch(chunks, V, T, Sn[:10])
+        assert rc == lc.LVN_ERR_CAPACITY and np.array_equal(res3["numSeamNodes"], res["numSeamNodes"])
+        # an empty batch, a batch of empty chunks
+        assert ctx.generateSimplifiedBatch(np.zeros((0, 4), np.int32), V, T, Sn)[0] == 0
+        rc, res4, _ = ctx.generateSimplifiedBatch([[0, 15 * 256, 0, 256]] * 3, V, T, Sn)
+        assert rc == 0 and res4["numTriangles"].sum() == 0
+    finally:
+        ctx.destroy()
