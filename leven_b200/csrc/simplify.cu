@@ -25,6 +25,7 @@
 // rotateq_xy (vtav[0][0] written twice, `cc + v`): the reference's results are the bar.
 // _mm_rsqrt_ps := 1 / sqrt(x) (arithmetic spec; the x86 estimate differs between CPU vendors).
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -34,7 +35,7 @@
 
 namespace lvn {
 
-constexpr int SIMP_BLOCK = 512;
+constexpr int SIMP_BLOCK = 1024;          // one block per mesh; 64 registers per thread
 constexpr int SIMP_WARPS = SIMP_BLOCK / 32;
 constexpr int SIMP_MAX_DEGREE = 16;      // COLLAPSE_MAX_DEGREE
 constexpr int SIMP_SLACK = 256;          // raw draws beyond numRandom that one iteration may consume on rejections
@@ -54,15 +55,17 @@ struct SimpJobDev {
 struct SimpScratch {
     float4 *vx, *vn, *vc;                // working vertices
     int *tri1;                           // the second triangle buffer (the first is the mesh's own slice), 3 ints each
-    uint2 *edge[2];                      // (min, max) ping-pong
-    int *vcount, *vstart, *vfill;        // per vertex: bucket count / start / cursor, later triangle counts
-    int *boundary, *target, *vscan;
+    uint2 *edge[2];                      // (min, max) ping-pong; the idle one also holds an iteration's candidate list
+    int *boundary;                       // per vertex: boundary mark, later the list of collapsing vertices
     unsigned long long *best;            // per vertex (error bits << 32 | edge)
+    int *vcount, *target;                // per vertex: triangle count, collapse target -- global fallbacks (vtxSmem == 0)
     const unsigned int *raw;             // mt19937(42) outputs
     int maskWords;                       // capacity of each of the two shared-memory word arrays
+    int vtxSmem;                         // capacity (vertices) of the two shared-memory per-vertex arrays, or 0
+    long long *timing;                   // LVN_SIMP_TIMING builds only
 };
 
-extern __shared__ unsigned int s_dyn[];  // [maskWords] ballot masks, [maskWords] exclusive prefix of their popcounts
+extern __shared__ unsigned int s_dyn[];  // [maskWords] ballot masks, [maskWords] exclusive prefix of their popcounts, [vtxSmem] triangle counts, [vtxSmem] targets
 
 // exclusive prefix of the popcounts of s_mask[0 .. nwords) into s_pref; returns the total (same in every thread)
 __device__ __forceinline__ int words_prefix(const unsigned int *s_mask, int *s_pref, int nwords, int *s_warp)
@@ -116,17 +119,30 @@ __device__ __forceinline__ int block_scan(const int *in, int *out, int n, int *s
     return carry;
 }
 
-// pass 1 of a stable compaction: s_mask[i / 32] bit (i % 32) = pred(i), i < n
-template <class Pred>
-__device__ __forceinline__ void ballot_pass(int n, unsigned int *s_mask, Pred pred)
+// pass 1 of a stable compaction: s_mask[i / 32] bit (i % 32) = pred(i), i < n.
+// The mesh lives in L2, not in shared memory, so a pass is bound by load latency, not bandwidth:
+// every thread takes U elements per round and issues all their loads (`load`, index clamped
+// instead of branched) and then all the dependent gathers (`gather`) before the first ballot.
+template <int U, class Load, class Gather, class Pred>
+__device__ __forceinline__ void ballot_pass(int n, unsigned int *s_mask, Load load, Gather gather, Pred pred)
 {
     const int tid = threadIdx.x;
     const int nr = (n + 31) & ~31;
-#pragma unroll 2
-    for (int i = tid; i < nr; i += SIMP_BLOCK) {
-        const bool p = i < n && pred(i);
-        const unsigned int m = __ballot_sync(0xffffffffu, p);
-        if ((tid & 31) == 0) s_mask[i >> 5] = m;
+    for (int base = tid; base < nr; base += SIMP_BLOCK * U) {
+        decltype(load(0)) a[U];
+        decltype(gather(0, a[0])) b[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) a[u] = load(min(base + u * SIMP_BLOCK, n - 1));
+#pragma unroll
+        for (int u = 0; u < U; u++) b[u] = gather(min(base + u * SIMP_BLOCK, n - 1), a[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * SIMP_BLOCK;
+            if (i < nr) {   // warp-uniform
+                const unsigned int m = __ballot_sync(0xffffffffu, i < n && pred(i, a[u], b[u]));
+                if ((tid & 31) == 0) s_mask[i >> 5] = m;
+            }
+        }
     }
 }
 // pass 2: where element i goes, or -1
@@ -316,6 +332,13 @@ __device__ __forceinline__ void raw_edge(const int *tri, int j, int &mn, int &mx
     mn = min(a, b); mx = max(a, b);
 }
 
+// LVN_SIMP_TIMING: thread 0 of every block accumulates clock64 per phase into ws.timing[block][16]
+#ifdef LVN_SIMP_TIMING
+#define PHASE(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long now_ = clock64(); ws.timing[blockIdx.x * 16 + ph_] += now_ - t_; t_ = now_; ph_ = (k); } } while (0)
+#else
+#define PHASE(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(SIMP_BLOCK)
 k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex *V, int *T, int4 *__restrict__ results)
 {
@@ -332,57 +355,71 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         if (tid == 0) results[job.result] = make_int4(NV, NT0, job.skip ? -2 : 0, 0);
         return;
     }
-    // an index outside the mesh's vertices would be a wild write below (the reference would crash):
-    // such a mesh is left untouched and reported with iterations = -1.  The same for a mesh whose
-    // ballot masks do not fit the shared memory of this launch (iterations = -2; host-side check).
-    const int NE0 = NT0 * 3;
-    if (tid == 0) { s_bad = 0; s_last = -1; }
-    __syncthreads();
-    for (int i = tid; i < NE0; i += SIMP_BLOCK) if ((unsigned int)tri[0][i] >= (unsigned int)NV) s_bad = 1;
-    __syncthreads();
-    if (s_bad) {
-        if (tid == 0) results[job.result] = make_int4(NV, NT0, -1, 0);
-        return;
-    }
+    // The two per-vertex arrays every pass gathers from -- the collapse target and the triangle
+    // count -- live in shared memory when the launch's largest mesh allows (ws.vtxSmem), so that a
+    // pass over triangles or edges has one global load per element and the count updates are
+    // shared-memory atomics.  Otherwise the same code runs on the global fallbacks.
+    int *vcount = ws.vtxSmem ? reinterpret_cast<int *>(s_dyn + 2 * ws.maskWords) : ws.vcount + job.vtxOff;
+    int *target = ws.vtxSmem ? vcount + ws.vtxSmem : ws.target + job.vtxOff;
     float4 *vx = ws.vx + job.vtxOff, *vn = ws.vn + job.vtxOff, *vc = ws.vc + job.vtxOff;
     uint2 *edge[2] = {ws.edge[0] + job.edgeOff, ws.edge[1] + job.edgeOff};
-    int *vcount = ws.vcount + job.vtxOff, *vstart = ws.vstart + job.vtxOff, *vfill = ws.vfill + job.vtxOff;
-    int *boundary = ws.boundary + job.vtxOff, *target = ws.target + job.vtxOff, *vscan = ws.vscan + job.vtxOff;
+    int *boundary = ws.boundary + job.vtxOff;        // BuildCandidateEdges; afterwards the list of collapsing vertices
     unsigned long long *best = ws.best + job.vtxOff;
     const float4 off = make_float4(job.offset[0], job.offset[1], job.offset[2], job.offset[3]);
+    const int NE0 = NT0 * 3;
+#ifdef LVN_SIMP_TIMING
+    long long t_ = clock64();
+    int ph_ = 0;
+#endif
 
     // ---- copy in; v.xyz -= worldSpaceOffset (ng_mesh_simplify.cpp:451-463) ----
+    if (tid == 0) { s_bad = 0; s_last = -1; }
     for (int i = tid; i < NV; i += SIMP_BLOCK) {
         const float4 *p = reinterpret_cast<const float4 *>(&meshV[i]);
         const float4 x = p[0];
         vx[i] = make_float4(x.x - off.x, x.y - off.y, x.z - off.z, x.w - off.w);
         vn[i] = p[1];
         vc[i] = p[2];
-        vcount[i] = 0; vfill[i] = 0; boundary[i] = 0;
+        vcount[i] = 0; boundary[i] = 0;
     }
     __syncthreads();
 
     // ---- BuildCandidateEdges (ng_mesh_simplify.cpp:122-177) ----
     // counting sort of the raw edges by max vertex ...
+    // An index outside the mesh's vertices would be a wild write (the reference would crash): such a
+    // mesh is left untouched and reported with iterations = -1.
+    int lmax = -1;
+#pragma unroll 4
     for (int j = tid; j < NE0; j += SIMP_BLOCK) {
         int mn, mx;
         raw_edge(tri[0], j, mn, mx);
+        if ((unsigned int)mn >= (unsigned int)NV || (unsigned int)mx >= (unsigned int)NV) { s_bad = 1; continue; }
         atomicAdd(&vcount[mx], 1);
-        atomicMax(&s_last, mx);     // the greatest max vertex: owner of the list's last run
+        lmax = max(lmax, mx);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if ((tid & 31) == 0) atomicMax(&s_last, lmax);     // the greatest max vertex: owner of the list's last run
     __syncthreads();
+    if (s_bad) {
+        if (tid == 0) results[job.result] = make_int4(NV, NT0, -1, 0);
+        return;
+    }
+    int *vstart = target;                              // (the collapse targets are not in use yet)
     block_scan(vcount, vstart, NV, s_warp);
+#pragma unroll 4
     for (int j = tid; j < NE0; j += SIMP_BLOCK) {
         int mn, mx;
         raw_edge(tri[0], j, mn, mx);
-        edge[1][vstart[mx] + atomicAdd(&vfill[mx], 1)] = make_uint2((unsigned int)mn, (unsigned int)mx);
+        edge[1][atomicAdd(&vstart[mx], 1)] = make_uint2((unsigned int)mn, (unsigned int)mx);   // vstart[v] ends as the bucket's end
     }
     __syncthreads();
+    PHASE(1);
     // ... then a rank sort by min inside each bucket (equal keys are interchangeable): edge[0] = std::sort's order
 #pragma unroll 2
     for (int p = tid; p < NE0; p += SIMP_BLOCK) {
         const uint2 e = edge[1][p];
-        const int st = vstart[e.y], n = vcount[e.y];
+        const int n = vcount[e.y], st = vstart[e.y] - n;
         int rank = 0;
         for (int q = 0; q < n; q++) {
             const unsigned int k = edge[1][st + q].x;
@@ -391,71 +428,114 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         edge[0][st + rank] = e;
     }
     __syncthreads();
+    PHASE(2);
     // runs of equal edges: a run of one marks both ends as boundary, a longer run is one filtered edge;
     // the last run of the list is never flushed by the reference's scan
     const int lastV = s_last;
     const unsigned int lastKey = edge[0][NE0 - 1].x;
-    ballot_pass(NE0, s_mask, [&](int p) {
-        const uint2 e = edge[0][p];
-        const bool start = p == 0 || edge[0][p - 1].x != e.x || edge[0][p - 1].y != e.y;
-        const bool more = p + 1 < NE0 && edge[0][p + 1].x == e.x && edge[0][p + 1].y == e.y;
-        const bool lastRun = (int)e.y == lastV && e.x == lastKey;
-        if (start && !more && !lastRun) { boundary[e.x] = 1; boundary[e.y] = 1; }
-        return start && more && !lastRun;
-    });
+    {
+        const uint2 *sorted = edge[0];
+        ballot_pass<4>(NE0, s_mask,
+            [&](int p) { return sorted[p]; },
+            [&](int p, uint2) { return make_uint4(sorted[max(p - 1, 0)].x, sorted[max(p - 1, 0)].y, sorted[min(p + 1, NE0 - 1)].x, sorted[min(p + 1, NE0 - 1)].y); },
+            [&](int p, uint2 e, uint4 nb) {
+                const bool start = p == 0 || nb.x != e.x || nb.y != e.y;
+                const bool more = p + 1 < NE0 && nb.z == e.x && nb.w == e.y;
+                const bool lastRun = (int)e.y == lastV && e.x == lastKey;
+                if (start && !more && !lastRun) { boundary[e.x] = 1; boundary[e.y] = 1; }
+                return start && more && !lastRun;
+            });
+    }
     __syncthreads();
     const int numFiltered = words_prefix(s_mask, s_pref, (NE0 + 31) >> 5, s_warp);
+#pragma unroll 4
     for (int p = tid; p < NE0; p += SIMP_BLOCK) {
+        const uint2 e = edge[0][p];
         const int o = compact_slot(s_mask, s_pref, p);
-        if (o >= 0) edge[1][o] = edge[0][p];
+        if (o >= 0) edge[1][o] = e;
     }
     __syncthreads();
-    ballot_pass(numFiltered, s_mask, [&](int i) { const uint2 e = edge[1][i]; return !boundary[e.x] && !boundary[e.y]; });
+    {
+        const uint2 *src = edge[1];
+        ballot_pass<4>(numFiltered, s_mask,
+            [&](int i) { return src[i]; },
+            [&](int, uint2 e) { return make_int2(boundary[e.x], boundary[e.y]); },
+            [&](int, uint2, int2 b) { return !b.x && !b.y; });
+    }
     __syncthreads();
     int NE = words_prefix(s_mask, s_pref, (numFiltered + 31) >> 5, s_warp);
+#pragma unroll 4
     for (int i = tid; i < numFiltered; i += SIMP_BLOCK) {
+        const uint2 e = edge[1][i];
         const int o = compact_slot(s_mask, s_pref, i);
-        if (o >= 0) edge[0][o] = edge[1][i];
+        if (o >= 0) edge[0][o] = e;
     }
+    PHASE(3);
     // vertexTriangleCounts (ng_mesh_simplify.cpp:478-489)
     for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
     __syncthreads();
+#pragma unroll 4
     for (int i = tid; i < NE0; i += SIMP_BLOCK) atomicAdd(&vcount[tri[0][i]], 1);
     __syncthreads();
 
     int NT = NT0, curT = 0, curE = 0;
     const int targetTriangleCount = (int)((float)NT0 * opt.targetPercentage);
     const float maxEdge2 = opt.maxEdgeSize * opt.maxEdgeSize;
+    int *list = boundary;
     int iterations = 0;
     while (NT > targetTriangleCount && iterations++ < opt.maxIterations) {
+        PHASE(4);
         for (int i = tid; i < NV; i += SIMP_BLOCK) { best[i] = ~0ull; target[i] = -1; }
         if (tid == 0) s_any = 0;
         // ---- FindValidCollapses (ng_mesh_simplify.cpp:181-283) ----
         const int numRandom = (int)((float)NE * opt.edgeFraction);
+        const uint2 *edges = edge[curE];
         if (numRandom > 0) {
             // std::uniform_int_distribution<int>(0, NE - 1) over std::mt19937(42), libstdc++:
             // product = raw * range; reject while (uint32)product < (2^32 - range) % range
             const unsigned int range = (unsigned int)NE, threshold = (0u - range) % range;
             const int K = numRandom + SIMP_SLACK;
-            ballot_pass(K, s_mask, [&](int k) { return (unsigned int)((unsigned long long)ws.raw[k] * range) >= threshold; });
+            ballot_pass<2>(K, s_mask,
+                [&](int k) { return ws.raw[k]; },
+                [&](int, unsigned int) { return 0; },
+                [&](int, unsigned int r, int) { return (unsigned int)((unsigned long long)r * range) >= threshold; });
             __syncthreads();
             words_prefix(s_mask, s_pref, (K + 31) >> 5, s_warp);
-            const uint2 *edges = edge[curE];
+            // the cheap tests first, on every draw; the survivors are gathered so that the QEF solves
+            // below run on full warps.  (A warp reads its own mask word -- the draw's place among the
+            // accepted ones -- before it overwrites that word with the survivors' mask.)
+            int *cand = reinterpret_cast<int *>(edge[curE ^ 1]);
+            ballot_pass<2>(K, s_mask,
+                [&](int k) {
+                    const int rank = compact_slot(s_mask, s_pref, k);
+                    const int i = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
+                    const uint2 e = edges[i];
+                    return make_int4((int)e.x, (int)e.y, i, rank >= 0 && rank < numRandom);
+                },
+                [&](int, int4 a) {
+                    const float4 nMin = vn[a.x], nMax = vn[a.y];
+                    const float4 pMin = vx[a.x], pMax = vx[a.y];
+                    const float mMin = vc[a.x].w, mMax = vc[a.y].w;
+                    const int degree = vcount[a.x] + vcount[a.y];
+                    const float4 d = make_float4(pMax.x - pMin.x, pMax.y - pMin.y, pMax.z - pMin.z, pMax.w - pMin.w);
+                    return !(dot4_lr(nMin, nMax) < opt.minAngleCosine) && !(dot4_lr(d, d) > maxEdge2) &&
+                           !((double)fabsf(mMin - mMax) > 1e-3) && !(degree > SIMP_MAX_DEGREE);
+                },
+                [&](int, int4 a, bool ok) { return a.w && ok; });
+            __syncthreads();
+            const int numCand = words_prefix(s_mask, s_pref, (K + 31) >> 5, s_warp);
 #pragma unroll 2
             for (int k = tid; k < K; k += SIMP_BLOCK) {
-                const int rank = compact_slot(s_mask, s_pref, k);       // this draw's place among the accepted ones
-                if (rank < 0 || rank >= numRandom) continue;
-                const int i = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
+                const int o = compact_slot(s_mask, s_pref, k);
+                if (o >= 0) cand[o] = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
+            }
+            __syncthreads();
+            for (int c = tid; c < numCand; c += SIMP_BLOCK) {
+                const int i = cand[c];
                 const uint2 e = edges[i];
                 const float4 nMin = vn[e.x], nMax = vn[e.y];
                 const float4 pMin = vx[e.x], pMax = vx[e.y];
-                const float mMin = vc[e.x].w, mMax = vc[e.y].w;
                 const int degree = vcount[e.x] + vcount[e.y];
-                if (dot4_lr(nMin, nMax) < opt.minAngleCosine) continue;
-                const float4 d = make_float4(pMax.x - pMin.x, pMax.y - pMin.y, pMax.z - pMin.z, pMax.w - pMin.w);
-                if (dot4_lr(d, d) > maxEdge2) continue;
-                if ((double)fabsf(mMin - mMax) > 1e-3) continue;
-                if (degree > SIMP_MAX_DEGREE) continue;
                 float pos[4];
                 float error = qef4_solve2(pMin, nMin, pMax, nMax, pos);
                 if (error > 0.f) error = 1.f / error;
@@ -470,15 +550,29 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         }
         __syncthreads();
         if (s_any == 0) break;
-        // ---- CollapseEdges (ng_mesh_simplify.cpp:287-311): one thread per min vertex ----
+        PHASE(5);
+        // ---- CollapseEdges (ng_mesh_simplify.cpp:287-311): an edge collapses when both its ends chose it;
+        //      the collapsing (min) vertices are gathered first, then each re-solves its 2-point QEF ----
+        ballot_pass<2>(NV, s_mask,
+            [&](int v) { return best[v]; },
+            [&](int, unsigned long long b) {
+                const uint2 e = edges[b == ~0ull ? 0 : (int)(unsigned int)b];
+                return make_uint4(e.x, e.y, (unsigned int)best[e.y], (unsigned int)(best[e.y] >> 32));
+            },
+            [&](int v, unsigned long long b, uint4 g) {
+                const unsigned long long bo = ((unsigned long long)g.w << 32) | g.z;
+                return b != ~0ull && (int)g.x == v && g.x != g.y && bo != ~0ull && (unsigned int)bo == (unsigned int)b;
+            });
+        __syncthreads();
+        const int numWin = words_prefix(s_mask, s_pref, (NV + 31) >> 5, s_warp);
         for (int v = tid; v < NV; v += SIMP_BLOCK) {
-            const unsigned long long b = best[v];
-            if (b == ~0ull) continue;
-            const int i = (int)(unsigned int)b;
-            const uint2 e = edge[curE][i];
-            if ((int)e.x != v || e.x == e.y) continue;
-            const unsigned long long bo = best[e.y];
-            if (bo == ~0ull || (int)(unsigned int)bo != i) continue;
+            const int o = compact_slot(s_mask, s_pref, v);
+            if (o >= 0) list[o] = v;
+        }
+        __syncthreads();
+        for (int w = tid; w < numWin; w += SIMP_BLOCK) {
+            const int v = list[w];
+            const uint2 e = edges[(int)(unsigned int)best[v]];
             float pos[4];
             const float4 nMin = vn[e.x], nMax = vn[e.y];
             qef4_solve2(vx[e.x], nMin, vx[e.y], nMax, pos);
@@ -487,81 +581,97 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
             vn[e.x] = make_float4((nMin.x - nMax.x) * 0.5f, (nMin.y - nMax.y) * 0.5f, (nMin.z - nMax.z) * 0.5f, (nMin.w - nMax.w) * 0.5f);
         }
         __syncthreads();
+        PHASE(6);
         // ---- RemoveTriangles (ng_mesh_simplify.cpp:315-360) and RemoveEdges (:364-391) ----
         // triangles first (their masks leave shared memory before the edges' masks enter)
         for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
         {
             const int *src = tri[curT];
-            ballot_pass(NT, s_mask, [&](int t) {
-                int a = src[t * 3], b = src[t * 3 + 1], c = src[t * 3 + 2];
-                const int ta = target[a], tb = target[b], tc = target[c];
-                if (ta != -1) a = ta;
-                if (tb != -1) b = tb;
-                if (tc != -1) c = tc;
-                return !(a == b || a == c || b == c);
-            });
+            ballot_pass<4>(NT, s_mask,
+                [&](int t) { return make_int3(src[t * 3], src[t * 3 + 1], src[t * 3 + 2]); },
+                [&](int, int3 v) { return make_int3(target[v.x], target[v.y], target[v.z]); },
+                [&](int, int3 v, int3 tg) {
+                    const int a = tg.x != -1 ? tg.x : v.x, b = tg.y != -1 ? tg.y : v.y, c = tg.z != -1 ? tg.z : v.z;
+                    return !(a == b || a == c || b == c);
+                });
             __syncthreads();
             const int newNT = words_prefix(s_mask, s_pref, (NT + 31) >> 5, s_warp);
             int *dst = tri[curT ^ 1];
-#pragma unroll 2
-            for (int t = tid; t < NT; t += SIMP_BLOCK) {
-                const int o = compact_slot(s_mask, s_pref, t);
-                if (o < 0) continue;
+            for (int base = tid; base < NT; base += SIMP_BLOCK * 4) {
+                int3 v[4], tg[4];
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    int idx = src[t * 3 + k];
-                    const int tg = target[idx];
-                    if (tg != -1) idx = tg;
-                    dst[o * 3 + k] = idx;
-                    atomicAdd(&vcount[idx], 1);
+                for (int u = 0; u < 4; u++) { const int t = min(base + u * SIMP_BLOCK, NT - 1); v[u] = make_int3(src[t * 3], src[t * 3 + 1], src[t * 3 + 2]); }
+#pragma unroll
+                for (int u = 0; u < 4; u++) tg[u] = make_int3(target[v[u].x], target[v[u].y], target[v[u].z]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int t = base + u * SIMP_BLOCK;
+                    const int o = t < NT ? compact_slot(s_mask, s_pref, t) : -1;
+                    if (o < 0) continue;
+                    const int a = tg[u].x != -1 ? tg[u].x : v[u].x, b = tg[u].y != -1 ? tg[u].y : v[u].y, c = tg[u].z != -1 ? tg[u].z : v[u].z;
+                    dst[o * 3] = a; dst[o * 3 + 1] = b; dst[o * 3 + 2] = c;
+                    atomicAdd(&vcount[a], 1); atomicAdd(&vcount[b], 1); atomicAdd(&vcount[c], 1);
                 }
             }
             __syncthreads();
             NT = newNT; curT ^= 1;
         }
+        PHASE(7);
         {
             const uint2 *src = edge[curE];
-            ballot_pass(NE, s_mask, [&](int i) {
-                uint2 e = src[i];
-                const int t0 = target[e.x], t1 = target[e.y];
-                if (t0 != -1) e.x = (unsigned int)t0;
-                if (t1 != -1) e.y = (unsigned int)t1;
-                return e.x != e.y;
-            });
+            ballot_pass<4>(NE, s_mask,
+                [&](int i) { return src[i]; },
+                [&](int, uint2 e) { return make_int2(target[e.x], target[e.y]); },
+                [&](int, uint2 e, int2 tg) {
+                    return (tg.x != -1 ? (unsigned int)tg.x : e.x) != (tg.y != -1 ? (unsigned int)tg.y : e.y);
+                });
             __syncthreads();
             const int newNE = words_prefix(s_mask, s_pref, (NE + 31) >> 5, s_warp);
             uint2 *dst = edge[curE ^ 1];
-#pragma unroll 2
-            for (int i = tid; i < NE; i += SIMP_BLOCK) {
-                const int o = compact_slot(s_mask, s_pref, i);
-                if (o < 0) continue;
-                uint2 e = src[i];
-                const int t0 = target[e.x], t1 = target[e.y];
-                if (t0 != -1) e.x = (unsigned int)t0;
-                if (t1 != -1) e.y = (unsigned int)t1;
-                dst[o] = e;
+            for (int base = tid; base < NE; base += SIMP_BLOCK * 4) {
+                uint2 e[4];
+                int2 tg[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) e[u] = src[min(base + u * SIMP_BLOCK, NE - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; u++) tg[u] = make_int2(target[e[u].x], target[e[u].y]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * SIMP_BLOCK;
+                    const int o = i < NE ? compact_slot(s_mask, s_pref, i) : -1;
+                    if (o < 0) continue;
+                    dst[o] = make_uint2(tg[u].x != -1 ? (unsigned int)tg[u].x : e[u].x, tg[u].y != -1 ? (unsigned int)tg[u].y : e[u].y);
+                }
             }
             __syncthreads();
             NE = newNE; curE ^= 1;
         }
     }
     __syncthreads();
+    PHASE(8);
 
     // ---- CompactVertices + write back (ng_mesh_simplify.cpp:395-437,520-539) ----
-    for (int i = tid; i < NV; i += SIMP_BLOCK) vfill[i] = 0;
+    int *used = target;
+    for (int i = tid; i < NV; i += SIMP_BLOCK) used[i] = 0;
     __syncthreads();
-    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) vfill[tri[curT][i]] = 1;
+#pragma unroll 4
+    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) used[tri[curT][i]] = 1;
     __syncthreads();
-    const int newNV = block_scan(vfill, vscan, NV, s_warp);
+    ballot_pass<4>(NV, s_mask, [&](int i) { return used[i]; }, [&](int, int) { return 0; }, [&](int, int u, int) { return u != 0; });
+    __syncthreads();
+    const int newNV = words_prefix(s_mask, s_pref, (NV + 31) >> 5, s_warp);
     for (int i = tid; i < NV; i += SIMP_BLOCK) {
-        if (!vfill[i]) continue;
-        float4 *p = reinterpret_cast<float4 *>(&meshV[vscan[i]]);
+        const int o = compact_slot(s_mask, s_pref, i);
+        if (o < 0) continue;
+        float4 *p = reinterpret_cast<float4 *>(&meshV[o]);
         const float4 x = vx[i];
         p[0] = make_float4(x.x + off.x, x.y + off.y, x.z + off.z, x.w + off.w);
         p[1] = vn[i];
         p[2] = vc[i];
     }
-    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) tri[0][i] = vscan[tri[curT][i]];   // each element read and written by one thread
+#pragma unroll 4
+    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) tri[0][i] = compact_slot(s_mask, s_pref, tri[curT][i]);   // each element read and written by one thread
+    PHASE(9);
     if (tid == 0) results[job.result] = make_int4(newNV, NT, iterations, NE);
 }
 
@@ -650,7 +760,7 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     if (n <= 0) return LVN_SUCCESS;
     std::vector<SimpJobDev> jd(n);
     long long edgeTotal = 0, vtxTotal = 0;
-    int maxElems = 0, maxDraws = 0;
+    int maxElems = 0, maxDraws = 0, maxVerts = 0;
     for (int m = 0; m < n; m++) {
         const SimplifyMesh &j = meshes[m];
         SimpJobDev &d = jd[m];
@@ -661,18 +771,24 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
         d.opt = j.opt;
         d.edgeOff = edgeTotal; d.vtxOff = (int)vtxTotal; d.result = m; d.skip = 0;
         if (j.numTriangles < 100 || j.numVertices < 100) continue;    // passes through: no scratch
+        // one iteration consumes at most numRandom + SIMP_SLACK raw draws; the ballot masks cover the raw
+        // edges, the draws and the vertices
         const double draws = (double)j.numTriangles * 3.0 * (double)j.opt.edgeFraction + SIMP_SLACK;
-        const double elems = std::max((double)j.numTriangles * 3.0, draws);
-        if (elems / 32.0 * 8.0 + 64 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // reported as iterations = -2
+        const double elems = std::max(std::max((double)j.numTriangles * 3.0, draws), (double)j.numVertices);
+        if ((elems / 32.0 + 64.0) * 8.0 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // reported as iterations = -2
         maxElems = std::max(maxElems, (int)elems);
         maxDraws = std::max(maxDraws, (int)draws);
-        edgeTotal += ((long long)j.numTriangles * 3 + 3) & ~3ll;
+        maxVerts = std::max(maxVerts, j.numVertices);
+        // the edge buffers hold 3 * numTriangles (min, max) pairs, or an iteration's candidate list (one int per draw)
+        edgeTotal += (std::max((long long)j.numTriangles * 3, ((long long)draws + 2) / 2) + 3) & ~3ll;
         vtxTotal += (j.numVertices + 3) & ~3;
         if (vtxTotal > 0x7fffffffll) return LVN_ERR_CAPACITY;
     }
     LV(ensure_raw(maxDraws));
     const int maskWords = ((maxElems + 31) / 32 + 31) & ~31;
-    const size_t smem = (size_t)maskWords * 8;
+    int vtxSmem = (maxVerts + 31) & ~31;
+    if ((size_t)maskWords * 8 + (size_t)vtxSmem * 8 > SIMP_MAX_SMEM) vtxSmem = 0;     // per-vertex arrays fall back to global memory
+    const size_t smem = (size_t)maskWords * 8 + (size_t)vtxSmem * 8;
     if (smem > 48 * 1024 && smem > g_simp.smemSet) {
         MCU(cudaFuncSetAttribute(k_simplify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMP_MAX_SMEM));
         g_simp.smemSet = SIMP_MAX_SMEM;
@@ -689,8 +805,8 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     auto take = [&](size_t bytes) { const size_t o = off; off += simp_align(bytes); return o; };
     const size_t oLaunch = take(sizeof(SimpJobDev) * n), oJobs = take(sizeof(SimpJobDev) * n),
                  oVx = take(16 * NVt), oVn = take(16 * NVt), oVc = take(16 * NVt), oT1 = take(4 * E),
-                 oE0 = take(8 * E), oE1 = take(8 * E), oVcnt = take(4 * NVt), oVst = take(4 * NVt), oVfl = take(4 * NVt),
-                 oBd = take(4 * NVt), oTg = take(4 * NVt), oVs = take(4 * NVt), oBest = take(8 * NVt);
+                 oE0 = take(8 * E), oE1 = take(8 * E), oVcnt = take(4 * NVt), oBd = take(4 * NVt), oTg = take(4 * NVt),
+                 oBest = take(8 * NVt);
     LV(ensure_buffer(&g_simp.d_blob, &g_simp.blobCap, off));
     char *B = (char *)g_simp.d_blob;
     MCU(cudaMemcpyAsync(B + oLaunch, launch.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
@@ -698,12 +814,32 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     ws.vx = (float4 *)(B + oVx); ws.vn = (float4 *)(B + oVn); ws.vc = (float4 *)(B + oVc);
     ws.tri1 = (int *)(B + oT1);
     ws.edge[0] = (uint2 *)(B + oE0); ws.edge[1] = (uint2 *)(B + oE1);
-    ws.vcount = (int *)(B + oVcnt); ws.vstart = (int *)(B + oVst); ws.vfill = (int *)(B + oVfl); ws.boundary = (int *)(B + oBd);
-    ws.target = (int *)(B + oTg); ws.vscan = (int *)(B + oVs); ws.best = (unsigned long long *)(B + oBest);
+    ws.vcount = (int *)(B + oVcnt); ws.boundary = (int *)(B + oBd); ws.target = (int *)(B + oTg);
+    ws.best = (unsigned long long *)(B + oBest);
     ws.raw = g_simp.d_raw;
     ws.maskWords = maskWords;
+    ws.vtxSmem = vtxSmem;
+    ws.timing = nullptr;
+#ifdef LVN_SIMP_TIMING
+    static long long *d_timing = nullptr;
+    if (!d_timing) MCU(cudaMalloc(&d_timing, sizeof(long long) * 16 * 65536));
+    MCU(cudaMemsetAsync(d_timing, 0, sizeof(long long) * 16 * n, st));
+    ws.timing = d_timing;
+#endif
     k_simplify<<<n, SIMP_BLOCK, smem, st>>>((const SimpJobDev *)(B + oLaunch), ws, d_V, d_T, d_results);
     MCU(cudaGetLastError());
+#ifdef LVN_SIMP_TIMING
+    {
+        std::vector<long long> t(16 * (size_t)n);
+        MCU(cudaMemcpyAsync(t.data(), d_timing, sizeof(long long) * 16 * n, cudaMemcpyDeviceToHost, st));
+        MCU(cudaStreamSynchronize(st));
+        static const char *names[10] = {"copy-in + bucket fill", "rank sort", "runs + filters", "triangle counts", "sample + QEF", "collapse", "triangles", "edges", "write back", ""};   // phase k ends at PHASE(k + 1)
+        long long sum[16] = {0};
+        for (int b = 0; b < n; b++) for (int k = 0; k < 16; k++) sum[k] += t[16 * (size_t)b + k];
+        fprintf(stderr, "[simplify timing] %d meshes; block 0 (largest: %d triangles) / mean over blocks, kilocycles\n", n, launch[0].numTriangles);
+        for (int k = 0; k < 9; k++) fprintf(stderr, "[simplify timing]   %-24s %9.1f %9.1f\n", names[k], t[k] / 1e3, sum[k] / 1e3 / n);
+    }
+#endif
     if (d_packV) {
         MCU(cudaMemcpyAsync(B + oJobs, jd.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
         k_pack_meshes<<<n, 256, 0, st>>>((const SimpJobDev *)(B + oJobs), d_results, n, d_V, d_T, d_packV, d_packT, d_packOffsets, d_packTotals);
