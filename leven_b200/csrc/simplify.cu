@@ -54,18 +54,18 @@ struct SimpJobDev {
 
 struct SimpScratch {
     float4 *vx, *vn, *vc;                // working vertices
-    int *tri1;                           // the second triangle buffer (the first is the mesh's own slice), 3 ints each
-    uint2 *edge[2];                      // (min, max) ping-pong; the idle one also holds an iteration's candidate list
-    int *boundary;                       // per vertex: boundary mark, later the list of collapsing vertices
+    int *tri1;                           // staging of the compacted triangle list, 3 ints each
+    uint2 *edge[2];                      // (min, max): sort buffers; then [0] the candidate edges, [1] a round's candidate list
+    int *boundary;                       // per vertex: boundary mark, later per-draw / per-vertex gather lists
     unsigned long long *best;            // per vertex (error bits << 32 | edge)
-    int *vcount, *target;                // per vertex: triangle count, collapse target -- global fallbacks (vtxSmem == 0)
+    int *rep, *vcount;                   // per vertex: representative, triangle count -- global fallbacks (vtxSmem == 0)
     const unsigned int *raw;             // mt19937(42) outputs
-    int maskWords;                       // capacity of each of the two shared-memory word arrays
+    int wordsE, wordsS;                  // capacities of the shared-memory mask / prefix word arrays
     int vtxSmem;                         // capacity (vertices) of the two shared-memory per-vertex arrays, or 0
     long long *timing;                   // LVN_SIMP_TIMING builds only
 };
 
-extern __shared__ unsigned int s_dyn[];  // [maskWords] ballot masks, [maskWords] exclusive prefix of their popcounts, [vtxSmem] triangle counts, [vtxSmem] targets
+extern __shared__ unsigned int s_dyn[];
 
 // exclusive prefix of the popcounts of s_mask[0 .. nwords) into s_pref; returns the total (same in every thread)
 __device__ __forceinline__ int words_prefix(const unsigned int *s_mask, int *s_pref, int nwords, int *s_warp)
@@ -332,6 +332,18 @@ __device__ __forceinline__ void raw_edge(const int *tri, int j, int &mn, int &mx
     mn = min(a, b); mx = max(a, b);
 }
 
+// the i-th set bit over the mask words (i < total): the word by binary search over the exclusive
+// prefix, the bit by __fns
+__device__ __forceinline__ int select_bit(const unsigned int *s_mask, const int *s_pref, int nwords, int i)
+{
+    int lo = 0, hi = nwords - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_pref[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return (lo << 5) + (int)__fns(s_mask[lo], 0, i - s_pref[lo] + 1);
+}
+
 // LVN_SIMP_TIMING: thread 0 of every block accumulates clock64 per phase into ws.timing[block][16]
 #ifdef LVN_SIMP_TIMING
 #define PHASE(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long now_ = clock64(); ws.timing[blockIdx.x * 16 + ph_] += now_ - t_; t_ = now_; ph_ = (k); } } while (0)
@@ -339,30 +351,43 @@ __device__ __forceinline__ void raw_edge(const int *tri, int j, int &mn, int &mx
 #define PHASE(k) do { } while (0)
 #endif
 
+// One block simplifies one mesh.  The reference rewrites and compacts its triangle and edge lists
+// after every round of collapses; here both lists stay as built and a per-vertex representative
+// (rep[v]: the vertex v has been merged into) stands for the rewriting: element k of a list is
+// alive while its ends' representatives differ, and "the i-th edge of the compacted list" -- what
+// the random candidate sample indexes -- is the i-th alive edge, found by a select over the
+// alive mask.  The lists are compacted once, at the end.
 __global__ void __launch_bounds__(SIMP_BLOCK)
 k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex *V, int *T, int4 *__restrict__ results)
 {
-    __shared__ int s_warp[SIMP_WARPS], s_any, s_last, s_bad;
-    unsigned int *s_mask = s_dyn;
-    int *s_pref = reinterpret_cast<int *>(s_dyn + ws.maskWords);
+    __shared__ int s_warp[SIMP_WARPS], s_any, s_last, s_bad, s_count;
+    // dynamic shared memory: [wordsE] alive-edge mask, [wordsE] its prefix, [wordsS] scratch mask, [wordsS] its
+    // prefix, then the two per-vertex arrays when they fit (ws.vtxSmem)
+    unsigned int *s_maskE = s_dyn;
+    int *s_prefE = reinterpret_cast<int *>(s_dyn + ws.wordsE);
+    unsigned int *s_mask = s_dyn + 2 * ws.wordsE;
+    int *s_pref = reinterpret_cast<int *>(s_mask + ws.wordsS);
     const SimpJobDev job = jobs[blockIdx.x];
     const lvn_simplify_options opt = job.opt;
     const int tid = threadIdx.x, NV = job.numVertices, NT0 = job.numTriangles;
     lvn_mesh_vertex *meshV = V + job.vertexOffset;
-    int *tri[2] = {T + (size_t)job.triangleOffset * 3, ws.tri1 + job.edgeOff};
+    int *tri = T + (size_t)job.triangleOffset * 3;
 
     if (job.skip || NT0 < 100 || NV < 100) {   // ng_mesh_simplify.cpp:446-449: too small, returned untouched
         if (tid == 0) results[job.result] = make_int4(NV, NT0, job.skip ? -2 : 0, 0);
         return;
     }
-    // The two per-vertex arrays every pass gathers from -- the collapse target and the triangle
-    // count -- live in shared memory when the launch's largest mesh allows (ws.vtxSmem), so that a
-    // pass over triangles or edges has one global load per element and the count updates are
-    // shared-memory atomics.  Otherwise the same code runs on the global fallbacks.
-    int *vcount = ws.vtxSmem ? reinterpret_cast<int *>(s_dyn + 2 * ws.maskWords) : ws.vcount + job.vtxOff;
-    int *target = ws.vtxSmem ? vcount + ws.vtxSmem : ws.target + job.vtxOff;
+    // The per-vertex arrays every pass gathers from live in shared memory when the launch's largest
+    // mesh allows (ws.vtxSmem): a pass over triangles or edges then has one global load per element
+    // and the count updates are shared-memory atomics.  Otherwise the same code runs on global fallbacks.
+    //   rep     the vertex this one has been merged into (itself while it lives)
+    //   vcount  triangles per vertex (FindValidCollapses' degree); between the sample and the next
+    //           triangle pass the same array holds the round's collapse targets
+    int *rep = ws.vtxSmem ? reinterpret_cast<int *>(s_pref + ws.wordsS) : ws.rep + job.vtxOff;
+    int *vcount = ws.vtxSmem ? rep + ws.vtxSmem : ws.vcount + job.vtxOff;
+    int *target = vcount;
     float4 *vx = ws.vx + job.vtxOff, *vn = ws.vn + job.vtxOff, *vc = ws.vc + job.vtxOff;
-    uint2 *edge[2] = {ws.edge[0] + job.edgeOff, ws.edge[1] + job.edgeOff};
+    uint2 *edgeA = ws.edge[0] + job.edgeOff, *edgeB = ws.edge[1] + job.edgeOff;
     int *boundary = ws.boundary + job.vtxOff;        // BuildCandidateEdges; afterwards the list of collapsing vertices
     unsigned long long *best = ws.best + job.vtxOff;
     const float4 off = make_float4(job.offset[0], job.offset[1], job.offset[2], job.offset[3]);
@@ -392,7 +417,7 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
 #pragma unroll 4
     for (int j = tid; j < NE0; j += SIMP_BLOCK) {
         int mn, mx;
-        raw_edge(tri[0], j, mn, mx);
+        raw_edge(tri, j, mn, mx);
         if ((unsigned int)mn >= (unsigned int)NV || (unsigned int)mx >= (unsigned int)NV) { s_bad = 1; continue; }
         atomicAdd(&vcount[mx], 1);
         lmax = max(lmax, mx);
@@ -405,96 +430,127 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         if (tid == 0) results[job.result] = make_int4(NV, NT0, -1, 0);
         return;
     }
-    int *vstart = target;                              // (the collapse targets are not in use yet)
+    int *vstart = rep;                                 // (not in use yet)
     block_scan(vcount, vstart, NV, s_warp);
 #pragma unroll 4
     for (int j = tid; j < NE0; j += SIMP_BLOCK) {
         int mn, mx;
-        raw_edge(tri[0], j, mn, mx);
-        edge[1][atomicAdd(&vstart[mx], 1)] = make_uint2((unsigned int)mn, (unsigned int)mx);   // vstart[v] ends as the bucket's end
+        raw_edge(tri, j, mn, mx);
+        edgeB[atomicAdd(&vstart[mx], 1)] = make_uint2((unsigned int)mn, (unsigned int)mx);   // vstart[v] ends as the bucket's end
     }
     __syncthreads();
     PHASE(1);
-    // ... then a rank sort by min inside each bucket (equal keys are interchangeable): edge[0] = std::sort's order
+    // ... then a rank sort by min inside each bucket (equal keys are interchangeable): edgeA = std::sort's order
 #pragma unroll 2
     for (int p = tid; p < NE0; p += SIMP_BLOCK) {
-        const uint2 e = edge[1][p];
+        const uint2 e = edgeB[p];
         const int n = vcount[e.y], st = vstart[e.y] - n;
         int rank = 0;
         for (int q = 0; q < n; q++) {
-            const unsigned int k = edge[1][st + q].x;
+            const unsigned int k = edgeB[st + q].x;
             rank += (k < e.x) || (k == e.x && st + q < p);
         }
-        edge[0][st + rank] = e;
+        edgeA[st + rank] = e;
     }
     __syncthreads();
     PHASE(2);
     // runs of equal edges: a run of one marks both ends as boundary, a longer run is one filtered edge;
     // the last run of the list is never flushed by the reference's scan
     const int lastV = s_last;
-    const unsigned int lastKey = edge[0][NE0 - 1].x;
-    {
-        const uint2 *sorted = edge[0];
-        ballot_pass<4>(NE0, s_mask,
-            [&](int p) { return sorted[p]; },
-            [&](int p, uint2) { return make_uint4(sorted[max(p - 1, 0)].x, sorted[max(p - 1, 0)].y, sorted[min(p + 1, NE0 - 1)].x, sorted[min(p + 1, NE0 - 1)].y); },
-            [&](int p, uint2 e, uint4 nb) {
-                const bool start = p == 0 || nb.x != e.x || nb.y != e.y;
-                const bool more = p + 1 < NE0 && nb.z == e.x && nb.w == e.y;
-                const bool lastRun = (int)e.y == lastV && e.x == lastKey;
-                if (start && !more && !lastRun) { boundary[e.x] = 1; boundary[e.y] = 1; }
-                return start && more && !lastRun;
-            });
-    }
+    const unsigned int lastKey = edgeA[NE0 - 1].x;
+    ballot_pass<4>(NE0, s_maskE,
+        [&](int p) { return edgeA[p]; },
+        [&](int p, uint2) { return make_uint4(edgeA[max(p - 1, 0)].x, edgeA[max(p - 1, 0)].y, edgeA[min(p + 1, NE0 - 1)].x, edgeA[min(p + 1, NE0 - 1)].y); },
+        [&](int p, uint2 e, uint4 nb) {
+            const bool start = p == 0 || nb.x != e.x || nb.y != e.y;
+            const bool more = p + 1 < NE0 && nb.z == e.x && nb.w == e.y;
+            const bool lastRun = (int)e.y == lastV && e.x == lastKey;
+            if (start && !more && !lastRun) { boundary[e.x] = 1; boundary[e.y] = 1; }
+            return start && more && !lastRun;
+        });
     __syncthreads();
-    const int numFiltered = words_prefix(s_mask, s_pref, (NE0 + 31) >> 5, s_warp);
+    const int numFiltered = words_prefix(s_maskE, s_prefE, (NE0 + 31) >> 5, s_warp);
 #pragma unroll 4
     for (int p = tid; p < NE0; p += SIMP_BLOCK) {
-        const uint2 e = edge[0][p];
-        const int o = compact_slot(s_mask, s_pref, p);
-        if (o >= 0) edge[1][o] = e;
+        const uint2 e = edgeA[p];
+        const int o = compact_slot(s_maskE, s_prefE, p);
+        if (o >= 0) edgeB[o] = e;
     }
     __syncthreads();
-    {
-        const uint2 *src = edge[1];
-        ballot_pass<4>(numFiltered, s_mask,
-            [&](int i) { return src[i]; },
-            [&](int, uint2 e) { return make_int2(boundary[e.x], boundary[e.y]); },
-            [&](int, uint2, int2 b) { return !b.x && !b.y; });
-    }
+    ballot_pass<4>(numFiltered, s_maskE,
+        [&](int i) { return edgeB[i]; },
+        [&](int, uint2 e) { return make_int2(boundary[e.x], boundary[e.y]); },
+        [&](int, uint2, int2 b) { return !b.x && !b.y; });
     __syncthreads();
-    int NE = words_prefix(s_mask, s_pref, (numFiltered + 31) >> 5, s_warp);
+    const int NEinit = words_prefix(s_maskE, s_prefE, (numFiltered + 31) >> 5, s_warp);
 #pragma unroll 4
     for (int i = tid; i < numFiltered; i += SIMP_BLOCK) {
-        const uint2 e = edge[1][i];
-        const int o = compact_slot(s_mask, s_pref, i);
-        if (o >= 0) edge[0][o] = e;
+        const uint2 e = edgeB[i];
+        const int o = compact_slot(s_maskE, s_prefE, i);
+        if (o >= 0) edgeA[o] = e;
     }
+    const uint2 *edges = edgeA;                        // the candidate edges, as built; never rewritten
+    const int wordsE = (NEinit + 31) >> 5;
+    __syncthreads();
     PHASE(3);
-    // vertexTriangleCounts (ng_mesh_simplify.cpp:478-489)
-    for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
-    __syncthreads();
-#pragma unroll 4
-    for (int i = tid; i < NE0; i += SIMP_BLOCK) atomicAdd(&vcount[tri[0][i]], 1);
-    __syncthreads();
 
-    int NT = NT0, curT = 0, curE = 0;
+    // alive edges: mask + prefix; returns their number (RemoveEdges, ng_mesh_simplify.cpp:364-391)
+    auto alive_edges = [&]() {
+        ballot_pass<4>(NEinit, s_maskE,
+            [&](int i) { return edges[i]; },
+            [&](int, uint2 e) { return make_int2(rep[e.x], rep[e.y]); },
+            [&](int, uint2, int2 r) { return r.x != r.y; });
+        __syncthreads();
+        return words_prefix(s_maskE, s_prefE, wordsE, s_warp);
+    };
+    // alive triangles: their number, and the triangle count of every vertex
+    // (RemoveTriangles, ng_mesh_simplify.cpp:315-360; vertexTriangleCounts :478-489)
+    auto alive_triangles = [&]() {
+        for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int base = tid; base < NT0; base += SIMP_BLOCK * 4) {
+            int3 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int t = min(base + u * SIMP_BLOCK, NT0 - 1); v[u] = make_int3(tri[t * 3], tri[t * 3 + 1], tri[t * 3 + 2]); }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int a = rep[v[u].x], b = rep[v[u].y], c = rep[v[u].z];
+                if (base + u * SIMP_BLOCK < NT0 && !(a == b || a == c || b == c)) {
+                    cnt++;
+                    atomicAdd(&vcount[a], 1); atomicAdd(&vcount[b], 1); atomicAdd(&vcount[c], 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((tid & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
+        __syncthreads();
+        return s_count;
+    };
+
+    for (int i = tid; i < NV; i += SIMP_BLOCK) rep[i] = i;
+    __syncthreads();
+    int NT = alive_triangles();
+    int NE = alive_edges();
     const int targetTriangleCount = (int)((float)NT0 * opt.targetPercentage);
     const float maxEdge2 = opt.maxEdgeSize * opt.maxEdgeSize;
     int *list = boundary;
+    int *cand = reinterpret_cast<int *>(edgeB);
     int iterations = 0;
     while (NT > targetTriangleCount && iterations++ < opt.maxIterations) {
         PHASE(4);
-        for (int i = tid; i < NV; i += SIMP_BLOCK) { best[i] = ~0ull; target[i] = -1; }
+        for (int i = tid; i < NV; i += SIMP_BLOCK) best[i] = ~0ull;
         if (tid == 0) s_any = 0;
         // ---- FindValidCollapses (ng_mesh_simplify.cpp:181-283) ----
         const int numRandom = (int)((float)NE * opt.edgeFraction);
-        const uint2 *edges = edge[curE];
         if (numRandom > 0) {
             // std::uniform_int_distribution<int>(0, NE - 1) over std::mt19937(42), libstdc++:
             // product = raw * range; reject while (uint32)product < (2^32 - range) % range
             const unsigned int range = (unsigned int)NE, threshold = (0u - range) % range;
             const int K = numRandom + SIMP_SLACK;
+            int *park = cand + K;
             ballot_pass<2>(K, s_mask,
                 [&](int k) { return ws.raw[k]; },
                 [&](int, unsigned int) { return 0; },
@@ -504,13 +560,13 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
             // the cheap tests first, on every draw; the survivors are gathered so that the QEF solves
             // below run on full warps.  (A warp reads its own mask word -- the draw's place among the
             // accepted ones -- before it overwrites that word with the survivors' mask.)
-            int *cand = reinterpret_cast<int *>(edge[curE ^ 1]);
             ballot_pass<2>(K, s_mask,
                 [&](int k) {
                     const int rank = compact_slot(s_mask, s_pref, k);
                     const int i = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
-                    const uint2 e = edges[i];
-                    return make_int4((int)e.x, (int)e.y, i, rank >= 0 && rank < numRandom);
+                    const int j = select_bit(s_maskE, s_prefE, wordsE, i);        // the i-th alive edge
+                    const uint2 e = edges[j];
+                    return make_int4(rep[e.x], rep[e.y], j, rank >= 0 && rank < numRandom);
                 },
                 [&](int, int4 a) {
                     const float4 nMin = vn[a.x], nMax = vn[a.y];
@@ -518,33 +574,39 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
                     const float mMin = vc[a.x].w, mMax = vc[a.y].w;
                     const int degree = vcount[a.x] + vcount[a.y];
                     const float4 d = make_float4(pMax.x - pMin.x, pMax.y - pMin.y, pMax.z - pMin.z, pMax.w - pMin.w);
-                    return !(dot4_lr(nMin, nMax) < opt.minAngleCosine) && !(dot4_lr(d, d) > maxEdge2) &&
-                           !((double)fabsf(mMin - mMax) > 1e-3) && !(degree > SIMP_MAX_DEGREE);
+                    return (!(dot4_lr(nMin, nMax) < opt.minAngleCosine) && !(dot4_lr(d, d) > maxEdge2) &&
+                            !((double)fabsf(mMin - mMax) > 1e-3) && !(degree > SIMP_MAX_DEGREE)) ? a.z : -1;
                 },
-                [&](int, int4 a, bool ok) { return a.w && ok; });
+                [&](int k, int4 a, int j) {
+                    const bool ok = a.w && j >= 0;
+                    if (ok) park[k] = j;          // (parked per draw; gathered below)
+                    return ok;
+                });
             __syncthreads();
             const int numCand = words_prefix(s_mask, s_pref, (K + 31) >> 5, s_warp);
 #pragma unroll 2
             for (int k = tid; k < K; k += SIMP_BLOCK) {
                 const int o = compact_slot(s_mask, s_pref, k);
-                if (o >= 0) cand[o] = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
+                if (o >= 0) cand[o] = park[k];
             }
             __syncthreads();
             for (int c = tid; c < numCand; c += SIMP_BLOCK) {
-                const int i = cand[c];
-                const uint2 e = edges[i];
-                const float4 nMin = vn[e.x], nMax = vn[e.y];
-                const float4 pMin = vx[e.x], pMax = vx[e.y];
-                const int degree = vcount[e.x] + vcount[e.y];
+                const int j = cand[c];
+                const uint2 e0 = edges[j];
+                const int x = rep[e0.x], y = rep[e0.y];
+                const float4 nMin = vn[x], nMax = vn[y];
+                const float4 pMin = vx[x], pMax = vx[y];
+                const int degree = vcount[x] + vcount[y];
                 float pos[4];
                 float error = qef4_solve2(pMin, nMin, pMax, nMax, pos);
                 if (error > 0.f) error = 1.f / error;
                 const int penalty = max(0, degree - 10);
                 error += (float)penalty * (opt.maxError * 0.1f);
                 if (error > opt.maxError) continue;
-                const unsigned long long pack = ((unsigned long long)__float_as_uint(error) << 32) | (unsigned int)i;
-                atomicMin(&best[e.x], pack);
-                atomicMin(&best[e.y], pack);
+                // "the first cheapest edge wins", edges visited in ascending order: the alive edges keep their order
+                const unsigned long long pack = ((unsigned long long)__float_as_uint(error) << 32) | (unsigned int)j;
+                atomicMin(&best[x], pack);
+                atomicMin(&best[y], pack);
                 s_any = 1;
             }
         }
@@ -556,13 +618,16 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         ballot_pass<2>(NV, s_mask,
             [&](int v) { return best[v]; },
             [&](int, unsigned long long b) {
-                const uint2 e = edges[b == ~0ull ? 0 : (int)(unsigned int)b];
-                return make_uint4(e.x, e.y, (unsigned int)best[e.y], (unsigned int)(best[e.y] >> 32));
+                const uint2 e0 = edges[b == ~0ull ? 0 : (int)(unsigned int)b];
+                const int x = rep[e0.x], y = rep[e0.y];
+                const unsigned long long bo = best[y];
+                return make_uint4((unsigned int)x, (unsigned int)y, (unsigned int)bo, (unsigned int)(bo >> 32));
             },
             [&](int v, unsigned long long b, uint4 g) {
                 const unsigned long long bo = ((unsigned long long)g.w << 32) | g.z;
                 return b != ~0ull && (int)g.x == v && g.x != g.y && bo != ~0ull && (unsigned int)bo == (unsigned int)b;
             });
+        for (int i = tid; i < NV; i += SIMP_BLOCK) target[i] = -1;       // (the degrees are no longer needed)
         __syncthreads();
         const int numWin = words_prefix(s_mask, s_pref, (NV + 31) >> 5, s_warp);
         for (int v = tid; v < NV; v += SIMP_BLOCK) {
@@ -572,91 +637,41 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         __syncthreads();
         for (int w = tid; w < numWin; w += SIMP_BLOCK) {
             const int v = list[w];
-            const uint2 e = edges[(int)(unsigned int)best[v]];
+            const uint2 e0 = edges[(int)(unsigned int)best[v]];
+            const int x = rep[e0.x], y = rep[e0.y];
             float pos[4];
-            const float4 nMin = vn[e.x], nMax = vn[e.y];
-            qef4_solve2(vx[e.x], nMin, vx[e.y], nMax, pos);
-            target[e.y] = (int)e.x;
-            vx[e.x] = make_float4(pos[0], pos[1], pos[2], 1.f);
-            vn[e.x] = make_float4((nMin.x - nMax.x) * 0.5f, (nMin.y - nMax.y) * 0.5f, (nMin.z - nMax.z) * 0.5f, (nMin.w - nMax.w) * 0.5f);
+            const float4 nMin = vn[x], nMax = vn[y];
+            qef4_solve2(vx[x], nMin, vx[y], nMax, pos);
+            target[y] = x;
+            vx[x] = make_float4(pos[0], pos[1], pos[2], 1.f);
+            vn[x] = make_float4((nMin.x - nMax.x) * 0.5f, (nMin.y - nMax.y) * 0.5f, (nMin.z - nMax.z) * 0.5f, (nMin.w - nMax.w) * 0.5f);
         }
         __syncthreads();
+        for (int i = tid; i < NV; i += SIMP_BLOCK) { const int t = target[rep[i]]; if (t != -1) rep[i] = t; }
+        __syncthreads();
         PHASE(6);
-        // ---- RemoveTriangles (ng_mesh_simplify.cpp:315-360) and RemoveEdges (:364-391) ----
-        // triangles first (their masks leave shared memory before the edges' masks enter)
-        for (int i = tid; i < NV; i += SIMP_BLOCK) vcount[i] = 0;
-        {
-            const int *src = tri[curT];
-            ballot_pass<4>(NT, s_mask,
-                [&](int t) { return make_int3(src[t * 3], src[t * 3 + 1], src[t * 3 + 2]); },
-                [&](int, int3 v) { return make_int3(target[v.x], target[v.y], target[v.z]); },
-                [&](int, int3 v, int3 tg) {
-                    const int a = tg.x != -1 ? tg.x : v.x, b = tg.y != -1 ? tg.y : v.y, c = tg.z != -1 ? tg.z : v.z;
-                    return !(a == b || a == c || b == c);
-                });
-            __syncthreads();
-            const int newNT = words_prefix(s_mask, s_pref, (NT + 31) >> 5, s_warp);
-            int *dst = tri[curT ^ 1];
-            for (int base = tid; base < NT; base += SIMP_BLOCK * 4) {
-                int3 v[4], tg[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) { const int t = min(base + u * SIMP_BLOCK, NT - 1); v[u] = make_int3(src[t * 3], src[t * 3 + 1], src[t * 3 + 2]); }
-#pragma unroll
-                for (int u = 0; u < 4; u++) tg[u] = make_int3(target[v[u].x], target[v[u].y], target[v[u].z]);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int t = base + u * SIMP_BLOCK;
-                    const int o = t < NT ? compact_slot(s_mask, s_pref, t) : -1;
-                    if (o < 0) continue;
-                    const int a = tg[u].x != -1 ? tg[u].x : v[u].x, b = tg[u].y != -1 ? tg[u].y : v[u].y, c = tg[u].z != -1 ? tg[u].z : v[u].z;
-                    dst[o * 3] = a; dst[o * 3 + 1] = b; dst[o * 3 + 2] = c;
-                    atomicAdd(&vcount[a], 1); atomicAdd(&vcount[b], 1); atomicAdd(&vcount[c], 1);
-                }
-            }
-            __syncthreads();
-            NT = newNT; curT ^= 1;
-        }
+        NT = alive_triangles();       // (zeroes the shared target / count array first)
         PHASE(7);
-        {
-            const uint2 *src = edge[curE];
-            ballot_pass<4>(NE, s_mask,
-                [&](int i) { return src[i]; },
-                [&](int, uint2 e) { return make_int2(target[e.x], target[e.y]); },
-                [&](int, uint2 e, int2 tg) {
-                    return (tg.x != -1 ? (unsigned int)tg.x : e.x) != (tg.y != -1 ? (unsigned int)tg.y : e.y);
-                });
-            __syncthreads();
-            const int newNE = words_prefix(s_mask, s_pref, (NE + 31) >> 5, s_warp);
-            uint2 *dst = edge[curE ^ 1];
-            for (int base = tid; base < NE; base += SIMP_BLOCK * 4) {
-                uint2 e[4];
-                int2 tg[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) e[u] = src[min(base + u * SIMP_BLOCK, NE - 1)];
-#pragma unroll
-                for (int u = 0; u < 4; u++) tg[u] = make_int2(target[e[u].x], target[e[u].y]);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = base + u * SIMP_BLOCK;
-                    const int o = i < NE ? compact_slot(s_mask, s_pref, i) : -1;
-                    if (o < 0) continue;
-                    dst[o] = make_uint2(tg[u].x != -1 ? (unsigned int)tg[u].x : e[u].x, tg[u].y != -1 ? (unsigned int)tg[u].y : e[u].y);
-                }
-            }
-            __syncthreads();
-            NE = newNE; curE ^= 1;
-        }
+        NE = alive_edges();
     }
     __syncthreads();
     PHASE(8);
 
-    // ---- CompactVertices + write back (ng_mesh_simplify.cpp:395-437,520-539) ----
-    int *used = target;
+    // ---- the one compaction: alive triangles in order, the vertices they use in order
+    //      (RemoveTriangles' list, CompactVertices + write back, ng_mesh_simplify.cpp:395-437,520-539) ----
+    int *used = vcount;
     for (int i = tid; i < NV; i += SIMP_BLOCK) used[i] = 0;
     __syncthreads();
-#pragma unroll 4
-    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) used[tri[curT][i]] = 1;
+    ballot_pass<4>(NT0, s_maskE,
+        [&](int t) { return make_int3(tri[t * 3], tri[t * 3 + 1], tri[t * 3 + 2]); },
+        [&](int, int3 v) { return make_int3(rep[v.x], rep[v.y], rep[v.z]); },
+        [&](int t, int3, int3 r) {
+            const bool alive = !(r.x == r.y || r.x == r.z || r.y == r.z);
+            if (alive) { used[r.x] = 1; used[r.y] = 1; used[r.z] = 1; }
+            return alive;
+        });
     __syncthreads();
+    words_prefix(s_maskE, s_prefE, (NT0 + 31) >> 5, s_warp);
     ballot_pass<4>(NV, s_mask, [&](int i) { return used[i]; }, [&](int, int) { return 0; }, [&](int, int u, int) { return u != 0; });
     __syncthreads();
     const int newNV = words_prefix(s_mask, s_pref, (NV + 31) >> 5, s_warp);
@@ -669,8 +684,18 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
         p[1] = vn[i];
         p[2] = vc[i];
     }
+    // a triangle moves towards the front of its own list: staged through scratch
+    int *stage = ws.tri1 + job.edgeOff;
+#pragma unroll 2
+    for (int t = tid; t < NT0; t += SIMP_BLOCK) {
+        const int o = compact_slot(s_maskE, s_prefE, t);
+        if (o < 0) continue;
+#pragma unroll
+        for (int k = 0; k < 3; k++) stage[o * 3 + k] = compact_slot(s_mask, s_pref, rep[tri[t * 3 + k]]);
+    }
+    __syncthreads();
 #pragma unroll 4
-    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) tri[0][i] = compact_slot(s_mask, s_pref, tri[curT][i]);   // each element read and written by one thread
+    for (int i = tid; i < NT * 3; i += SIMP_BLOCK) tri[i] = stage[i];
     PHASE(9);
     if (tid == 0) results[job.result] = make_int4(newNV, NT, iterations, NE);
 }
@@ -760,7 +785,7 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     if (n <= 0) return LVN_SUCCESS;
     std::vector<SimpJobDev> jd(n);
     long long edgeTotal = 0, vtxTotal = 0;
-    int maxElems = 0, maxDraws = 0, maxVerts = 0;
+    int maxEdges = 0, maxOther = 0, maxDraws = 0, maxVerts = 0;
     for (int m = 0; m < n; m++) {
         const SimplifyMesh &j = meshes[m];
         SimpJobDev &d = jd[m];
@@ -771,24 +796,25 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
         d.opt = j.opt;
         d.edgeOff = edgeTotal; d.vtxOff = (int)vtxTotal; d.result = m; d.skip = 0;
         if (j.numTriangles < 100 || j.numVertices < 100) continue;    // passes through: no scratch
-        // one iteration consumes at most numRandom + SIMP_SLACK raw draws; the ballot masks cover the raw
-        // edges, the draws and the vertices
+        // one iteration consumes at most numRandom + SIMP_SLACK raw draws
         const double draws = (double)j.numTriangles * 3.0 * (double)j.opt.edgeFraction + SIMP_SLACK;
-        const double elems = std::max(std::max((double)j.numTriangles * 3.0, draws), (double)j.numVertices);
-        if ((elems / 32.0 + 64.0) * 8.0 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // reported as iterations = -2
-        maxElems = std::max(maxElems, (int)elems);
+        const double other = std::max(draws, (double)j.numVertices);
+        // shared memory: mask + prefix words over the raw edges, and over the draws / the vertices
+        if (((double)j.numTriangles * 3.0 / 32.0 + other / 32.0 + 128.0) * 8.0 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // iterations = -2
+        maxEdges = std::max(maxEdges, j.numTriangles * 3);
+        maxOther = std::max(maxOther, (int)other);
         maxDraws = std::max(maxDraws, (int)draws);
         maxVerts = std::max(maxVerts, j.numVertices);
-        // the edge buffers hold 3 * numTriangles (min, max) pairs, or an iteration's candidate list (one int per draw)
-        edgeTotal += (std::max((long long)j.numTriangles * 3, ((long long)draws + 2) / 2) + 3) & ~3ll;
+        // the edge buffers hold 3 * numTriangles (min, max) pairs; the second one later a round's draws (two ints each)
+        edgeTotal += (std::max((long long)j.numTriangles * 3, (long long)draws + 1) + 3) & ~3ll;
         vtxTotal += (j.numVertices + 3) & ~3;
         if (vtxTotal > 0x7fffffffll) return LVN_ERR_CAPACITY;
     }
     LV(ensure_raw(maxDraws));
-    const int maskWords = ((maxElems + 31) / 32 + 31) & ~31;
+    const int wordsE = ((maxEdges + 31) / 32 + 31) & ~31, wordsS = ((maxOther + 31) / 32 + 31) & ~31;
     int vtxSmem = (maxVerts + 31) & ~31;
-    if ((size_t)maskWords * 8 + (size_t)vtxSmem * 8 > SIMP_MAX_SMEM) vtxSmem = 0;     // per-vertex arrays fall back to global memory
-    const size_t smem = (size_t)maskWords * 8 + (size_t)vtxSmem * 8;
+    if (((size_t)wordsE + wordsS + vtxSmem) * 8 > SIMP_MAX_SMEM) vtxSmem = 0;     // per-vertex arrays fall back to global memory
+    const size_t smem = ((size_t)wordsE + wordsS + vtxSmem) * 8;
     if (smem > 48 * 1024 && smem > g_simp.smemSet) {
         MCU(cudaFuncSetAttribute(k_simplify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMP_MAX_SMEM));
         g_simp.smemSet = SIMP_MAX_SMEM;
@@ -814,10 +840,10 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     ws.vx = (float4 *)(B + oVx); ws.vn = (float4 *)(B + oVn); ws.vc = (float4 *)(B + oVc);
     ws.tri1 = (int *)(B + oT1);
     ws.edge[0] = (uint2 *)(B + oE0); ws.edge[1] = (uint2 *)(B + oE1);
-    ws.vcount = (int *)(B + oVcnt); ws.boundary = (int *)(B + oBd); ws.target = (int *)(B + oTg);
+    ws.vcount = (int *)(B + oVcnt); ws.boundary = (int *)(B + oBd); ws.rep = (int *)(B + oTg);
     ws.best = (unsigned long long *)(B + oBest);
     ws.raw = g_simp.d_raw;
-    ws.maskWords = maskWords;
+    ws.wordsE = wordsE; ws.wordsS = wordsS;
     ws.vtxSmem = vtxSmem;
     ws.timing = nullptr;
 #ifdef LVN_SIMP_TIMING
