@@ -67,6 +67,19 @@ struct SimpScratch {
 
 extern __shared__ unsigned int s_dyn[];
 
+// from the per-warp sums of a round: the sum of the warps before mine, and of all (SIMP_WARPS == 32:
+// every warp scans the 32 sums with shuffles instead of reading them all)
+static_assert(SIMP_WARPS == 32, "warp_totals scans one warp-sum per lane");
+__device__ __forceinline__ void warp_totals(const int *s_warp, int lane, int warp, int &before, int &total)
+{
+    const int v = s_warp[lane];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    before = __shfl_sync(0xffffffffu, incl - v, warp);
+    total = __shfl_sync(0xffffffffu, incl, 31);
+}
+
 // exclusive prefix of the popcounts of s_mask[0 .. nwords) into s_pref; returns the total (same in every thread)
 __device__ __forceinline__ int words_prefix(const unsigned int *s_mask, int *s_pref, int nwords, int *s_warp)
 {
@@ -80,9 +93,8 @@ __device__ __forceinline__ int words_prefix(const unsigned int *s_mask, int *s_p
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int q = 0; q < SIMP_WARPS; q++) { const int v = s_warp[q]; if (q < warp) woff += v; tot += v; }
+        int woff, tot;
+        warp_totals(s_warp, lane, warp, woff, tot);
         if (w < nwords) s_pref[w] = carry + woff + incl - c;
         carry += tot;
         __syncthreads();
@@ -107,9 +119,8 @@ __device__ __forceinline__ int block_scan(const int *in, int *out, int n, int *s
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int q = 0; q < SIMP_WARPS; q++) { const int t = s_warp[q]; if (q < warp) woff += t; tot += t; }
+        int woff, tot;
+        warp_totals(s_warp, lane, warp, woff, tot);
         int run = carry + woff + incl - sum;
 #pragma unroll
         for (int k = 0; k < 4; k++) { if (i + k < n) out[i + k] = run; run += v[k]; }
@@ -325,13 +336,6 @@ __device__ __forceinline__ float dot4_lr(const float4 a, const float4 b)   // GL
     return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }
 
-__device__ __forceinline__ void raw_edge(const int *tri, int j, int &mn, int &mx)
-{   // raw edge j of the triangle list: (0,1), (1,2), (0,2) of triangle j / 3 (ng_mesh_simplify.cpp:127-133)
-    const int t = j / 3, k = j - t * 3;
-    const int a = tri[t * 3 + (k == 2 ? 0 : k)], b = tri[t * 3 + (k == 0 ? 1 : 2)];
-    mn = min(a, b); mx = max(a, b);
-}
-
 // the i-th set bit over the mask words (i < total): the word by binary search over the exclusive
 // prefix, the bit by __fns
 __device__ __forceinline__ int select_bit(const unsigned int *s_mask, const int *s_pref, int nwords, int i)
@@ -415,12 +419,11 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
     // mesh is left untouched and reported with iterations = -1.
     int lmax = -1;
 #pragma unroll 4
-    for (int j = tid; j < NE0; j += SIMP_BLOCK) {
-        int mn, mx;
-        raw_edge(tri, j, mn, mx);
-        if ((unsigned int)mn >= (unsigned int)NV || (unsigned int)mx >= (unsigned int)NV) { s_bad = 1; continue; }
-        atomicAdd(&vcount[mx], 1);
-        lmax = max(lmax, mx);
+    for (int t = tid; t < NT0; t += SIMP_BLOCK) {      // a triangle's raw edges: (0,1), (1,2), (0,2) (ng_mesh_simplify.cpp:127-133)
+        const int a = tri[t * 3], b = tri[t * 3 + 1], c = tri[t * 3 + 2];
+        if ((unsigned int)a >= (unsigned int)NV || (unsigned int)b >= (unsigned int)NV || (unsigned int)c >= (unsigned int)NV) { s_bad = 1; continue; }
+        atomicAdd(&vcount[max(a, b)], 1); atomicAdd(&vcount[max(b, c)], 1); atomicAdd(&vcount[max(a, c)], 1);
+        lmax = max(lmax, max(a, max(b, c)));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -433,10 +436,11 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
     int *vstart = rep;                                 // (not in use yet)
     block_scan(vcount, vstart, NV, s_warp);
 #pragma unroll 4
-    for (int j = tid; j < NE0; j += SIMP_BLOCK) {
-        int mn, mx;
-        raw_edge(tri, j, mn, mx);
-        edgeB[atomicAdd(&vstart[mx], 1)] = make_uint2((unsigned int)mn, (unsigned int)mx);   // vstart[v] ends as the bucket's end
+    for (int t = tid; t < NT0; t += SIMP_BLOCK) {      // vstart[v] ends as the bucket's end
+        const int a = tri[t * 3], b = tri[t * 3 + 1], c = tri[t * 3 + 2];
+        edgeB[atomicAdd(&vstart[max(a, b)], 1)] = make_uint2((unsigned int)min(a, b), (unsigned int)max(a, b));
+        edgeB[atomicAdd(&vstart[max(b, c)], 1)] = make_uint2((unsigned int)min(b, c), (unsigned int)max(b, c));
+        edgeB[atomicAdd(&vstart[max(a, c)], 1)] = make_uint2((unsigned int)min(a, c), (unsigned int)max(a, c));
     }
     __syncthreads();
     PHASE(1);
