@@ -308,6 +308,60 @@ int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChunks, const i
                                           lvn_seam_node_info *seamNodes, int64_t seamCapacity,
                                           lvn_chunk_result *results, lvn_simplify_result *simplified);
 
+/* Clipmap::loadCollisionNodes' per-node work (clipmap.cpp:1346-1385) for many collision nodes in one
+ * pass: ConstructCollisionNodeData (clipmap.cpp:472-504: generateChunkMesh on the physics context at
+ * COLLISION_NODE_SIZE + ngMeshSimplifier) and the conversion AddMeshToWorldImpl makes for Bullet's
+ * btIndexedMesh (physics.cpp:549-573): physicsVertices[i] = (vertex.xyz - vec4(origin, 0)) * physicsScale,
+ * one vec4 (4 floats) per vertex, origin = min + size / 2; triangles = 3 ints each.  (The reference
+ * leaves a TODO there: "vertices and triangles should be created on the GPU".)  `vertices` (may be
+ * NULL) additionally receives the MeshVertex form the debug renderer is given (physics.cpp:706).
+ * Everything else as lvn_meshgen_generate_simplified_batch. */
+int lvn_meshgen_generate_collision_batch(lvn_meshgen *ctx, int nNodes, const int32_t *nodeMinSize,
+                                         const lvn_simplify_options *unitOptions, float physicsScale /* PHYSICS_SCALE = 0.05f, physics.cpp:79 */,
+                                         float *physicsVertices, lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                         int32_t *triangles, int64_t triangleCapacity,
+                                         lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                         lvn_chunk_result *results, lvn_simplify_result *simplified);
+
+/* ---- one Clipmap::update as two batched passes --------------------------- */
+
+/* A clipmap node as the update sees it: ClipmapNode::min_ / size_ (clipmap.cpp) and where its
+ * SeamNodeInfo records (ClipmapNode::seamNodes / numSeamNodes) lie in the caller's seam-node arena. */
+typedef struct lvn_clipmap_node {
+    int32_t min[3];
+    int32_t size;
+    int32_t firstSeamNode, numSeamNodes;
+} lvn_clipmap_node;
+
+typedef struct lvn_clipmap_update_totals {
+    int64_t nodeVertices, nodeTriangles;     /* the constructed nodes' (simplified) meshes: arenas [0, ..) */
+    int64_t seamVertices, seamTriangles;     /* the seam meshes: arenas [nodeVertices, ..), [nodeTriangles, ..) */
+    int64_t seamNodesUsed;                   /* the seam-node arena's fill after the update */
+    int32_t numConstructedActive;            /* constructed nodes with a mesh or seam nodes (the others are empty) */
+    int32_t numSeamUpdates;                  /* seam meshes regenerated = entries of seamUpdateNodes / seamResults */
+} lvn_clipmap_update_totals;
+
+/* The GPU work of one Clipmap::update (clipmap.cpp:1253-1340) in two batched passes:
+ *   nodes[0 .. numActive)                          the nodes active before the update, with their seam-node slices
+ *   nodes[numActive .. numActive + numConstruct)   the nodes the update loads ("filteredNodes"); on return
+ *                                                  their seam-node slices are filled in (appended to the arena)
+ * Pass 1 = ConstructClipmapNodeData for every node to load (lvn_meshgen_generate_simplified_batch;
+ * constructResults[i] addresses node numActive + i's mesh).  A node with a mesh or seam nodes
+ * becomes active (clipmap.cpp:1269).  Pass 2 = the seam-update set -- every active node found
+ * around the 8 cells min - CHILD_MIN_OFFSETS[i] * size of a newly active node (clipmap.cpp:1306-1324)
+ * -- and GenerateClipmapSeamMesh (clipmap.cpp:573-611) for all of them in one launch:
+ * seamUpdateNodes[u] = index into nodes (ascending), seamResults[u] its seam mesh (offsets into the
+ * same two arenas, after the node meshes).  Which nodes exist, are active or get loaded stays
+ * the caller's decision.  On LVN_ERR_CAPACITY totals says what pass 1 needs. */
+int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *nodes, int numActive, int numConstruct,
+                             const lvn_simplify_options *unitOptions,
+                             lvn_seam_node_info *seamNodes, int64_t seamNodesUsed, int64_t seamCapacity,
+                             lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                             lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                             lvn_chunk_result *constructResults,
+                             int32_t *seamUpdateNodes, lvn_seam_result *seamResults, const float seamColour[3],
+                             lvn_clipmap_update_totals *totals);
+
 /* ---- utilities of the path (a9, a15), usable on their own ---------------- */
 
 /* FindNextPrime, primes.h (primes.cpp:32-59) */

@@ -134,6 +134,8 @@ ABI = {
     "lvn_mesh_simplify_batch": (_I, [_I, _P, _P, _I, _P, _I64, _P, _I64, _P]),
     "lvn_mesh_simplify_last_error": (C.c_char_p, []),
     "lvn_meshgen_generate_simplified_batch": (_I, [_P, _I, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
+    "lvn_clipmap_update_batch": (_I, [_P, _P, _I, _I, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _P]),
+    "lvn_meshgen_generate_collision_batch": (_I, [_P, _I, _P, _P, C.c_float, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
 }
 
 _lib = None
@@ -330,6 +332,22 @@ class Compute_MeshGenContext:
         rc = self._L.lvn_meshgen_generate_simplified_batch(self.privateCtx_, len(ms), _ptr(ms), C.byref(opt),
                                                            _ptr(vertices), len(vertices), _ptr(triangles), len(triangles),
                                                            _ptr(seamNodes), len(seamNodes), _ptr(results), _ptr(simp))
+        return rc, results, simp
+
+    def generateCollisionBatch(self, nodeMinSize, physicsVertices, triangles, seamNodes, vertices=None, unitOptions=None,
+                               physicsScale=0.05):
+        """Clipmap::loadCollisionNodes' per-node work (clipmap.cpp:1346-1385) over a batch: ConstructCollisionNodeData
+        + AddMeshToWorldImpl's conversion (physics.cpp:549-573).  physicsVertices: float32[n][4]; triangles int32[n][3].
+        Returns (error, results, simplified)"""
+        ms = np.ascontiguousarray(nodeMinSize, np.int32).reshape(-1, 4)
+        results = np.zeros(len(ms), ChunkResult)
+        simp = np.zeros(len(ms), SimplifyResult)
+        opt = unitOptions if unitOptions is not None else SimplifyOptions.clipmap_unit()
+        assert vertices is None or len(vertices) >= len(physicsVertices)
+        rc = self._L.lvn_meshgen_generate_collision_batch(self.privateCtx_, len(ms), _ptr(ms), C.byref(opt), physicsScale,
+                                                          _ptr(physicsVertices), _ptr(vertices), len(physicsVertices),
+                                                          _ptr(triangles), len(triangles), _ptr(seamNodes), len(seamNodes),
+                                                          _ptr(results), _ptr(simp))
         return rc, results, simp
 
     def applyCSGOperationsBatch(self, opInfo, chunkMinSize):
@@ -635,3 +653,30 @@ def ngMeshSimplifierBatch(meshes, options):
     out = [(V[j["vertexOffset"]:j["vertexOffset"] + r["numVertices"]].copy(),
             T[j["triangleOffset"]:j["triangleOffset"] + r["numTriangles"]].copy()) for j, r in zip(jobs, res)]
     return rc, out, res
+
+
+# ---------------------------------------------------------------------------------------------
+# one Clipmap::update as two batched passes (clipmap.cpp:1253-1340)
+# ---------------------------------------------------------------------------------------------
+ClipmapNode = np.dtype([("min", np.int32, 3), ("size", np.int32), ("firstSeamNode", np.int32), ("numSeamNodes", np.int32)])
+
+
+class ClipmapUpdateTotals(C.Structure):
+    _fields_ = [("nodeVertices", C.c_int64), ("nodeTriangles", C.c_int64), ("seamVertices", C.c_int64), ("seamTriangles", C.c_int64),
+                ("seamNodesUsed", C.c_int64), ("numConstructedActive", C.c_int32), ("numSeamUpdates", C.c_int32)]
+
+
+def ClipmapUpdateBatch(ctx, nodes, numActive, seamNodes, seamNodesUsed, vertices, triangles, unitOptions=None, colour=(1.0, 1.0, 1.0)):
+    """lvn_clipmap_update_batch: nodes = ClipmapNode[numActive + numConstruct] (updated in place);
+    -> (rc, constructResults, seamUpdateNodes, seamResults, totals)"""
+    n_construct = len(nodes) - numActive
+    cres = np.zeros(max(n_construct, 1), ChunkResult)
+    upd = np.zeros(max(len(nodes), 1), np.int32)
+    sres = np.zeros(max(len(nodes), 1), SeamResult)
+    tot = ClipmapUpdateTotals()
+    opt = unitOptions if unitOptions is not None else SimplifyOptions.clipmap_unit()
+    col = (C.c_float * 3)(*colour)
+    rc = lib().lvn_clipmap_update_batch(ctx.privateCtx_, _ptr(nodes), int(numActive), int(n_construct), C.byref(opt),
+                                        _ptr(seamNodes), int(seamNodesUsed), len(seamNodes), _ptr(vertices), len(vertices),
+                                        _ptr(triangles), len(triangles), _ptr(cres), _ptr(upd), _ptr(sres), col, C.byref(tot))
+    return rc, cres[:n_construct], upd[:tot.numSeamUpdates], sres[:tot.numSeamUpdates], tot

@@ -424,6 +424,7 @@ struct lvn_meshgen {
     DevBuf<int4> d_simpRes;
     DevBuf<int2> d_packOff;
     DevBuf<lvn_mesh_vertex> d_packV;
+    DevBuf<float4> d_packP;
     DevBuf<int> d_packT;
     PinBuf<int4> h_simpRes;
     PinBuf<int2> h_packOff;
@@ -523,6 +524,8 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
     ctx->d_ops.release(); ctx->d_csgChunks.release();
+    ctx->d_simpRes.release(); ctx->d_packOff.release(); ctx->d_packV.release(); ctx->d_packP.release(); ctx->d_packT.release();
+    ctx->h_simpRes.release(); ctx->h_packOff.release();
     ctx->h_descs.release(); ctx->h_hdrs.release(); ctx->h_colOrigins.release();
     ctx->h_small.release();
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1134,13 +1137,14 @@ extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const i
 
 // ConstructClipmapNodeData / ConstructCollisionNodeData (clipmap.cpp:432-504) for many nodes:
 // generateChunkMesh, then ngMeshSimplifier with the options the clipmap derives from the node size.
-// The meshes stay in HBM between the two; only the simplified meshes cross PCIe.
-extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
-                                                     const lvn_simplify_options *unitOptions,
-                                                     lvn_mesh_vertex *vertices, int64_t vertexCapacity,
-                                                     lvn_mesh_triangle *triangles, int64_t triangleCapacity,
-                                                     lvn_seam_node_info *seamNodes, int64_t seamCapacity,
-                                                     lvn_chunk_result *results, lvn_simplify_result *simplified)
+// The meshes stay in HBM between the two; only the simplified meshes cross PCIe -- as MeshVertex
+// (`vertices`) and / or in the physics engine's format (`physicsVertices`, AddMeshToWorldImpl).
+static int generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                               const lvn_simplify_options *unitOptions,
+                               lvn_mesh_vertex *vertices, float *physicsVertices, float physicsScale, int64_t vertexCapacity,
+                               lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                               lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                               lvn_chunk_result *results, lvn_simplify_result *simplified)
 {
     if (!results || !unitOptions) return LVN_ERR_INVALID_VALUE;
     BatchOpts opts;
@@ -1176,12 +1180,14 @@ extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChun
     if (M > 0) {
         LV(ctx->d_simpRes.reserve(M));
         LV(ctx->d_packOff.reserve((size_t)M + 1));
-        LV(ctx->d_packV.reserve(ctx->lastCounters.nodes));
+        if (vertices) LV(ctx->d_packV.reserve(ctx->lastCounters.nodes));
+        if (physicsVertices) LV(ctx->d_packP.reserve(ctx->lastCounters.nodes));
         LV(ctx->d_packT.reserve(6 * (size_t)ctx->lastCounters.quads));
         LV(ctx->h_simpRes.reserve(M));
         LV(ctx->h_packOff.reserve((size_t)M + 1));
         const int rc = simplify_device(M, meshes.data(), ctx->d_vertices.p, ctx->d_tris.p, ctx->d_simpRes.p,
-                                       ctx->d_packV.p, ctx->d_packT.p, ctx->d_packOff.p, ctx->d_packOff.p + M, st);
+                                       vertices ? ctx->d_packV.p : nullptr, ctx->d_packT.p, ctx->d_packOff.p, ctx->d_packOff.p + M, st,
+                                       physicsVertices ? ctx->d_packP.p : nullptr, physicsScale);
         if (rc < 0) { g_lastCudaError = simplify_last_error(); return rc; }
         CU(cudaMemcpyAsync(ctx->h_simpRes.p, ctx->d_simpRes.p, sizeof(int4) * M, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ctx->h_packOff.p, ctx->d_packOff.p, sizeof(int2) * ((size_t)M + 1), cudaMemcpyDeviceToHost, st));
@@ -1213,11 +1219,37 @@ extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChun
     }
     // on LVN_ERR_CAPACITY the counts say what the caller must provide
     if (!seamsFit || totals.x > vertexCapacity || totals.y > triangleCapacity ||
-        (totals.x > 0 && !vertices) || (totals.y > 0 && !triangles)) return LVN_ERR_CAPACITY;
-    if (totals.x) CU(cudaMemcpyAsync(vertices, ctx->d_packV.p, sizeof(lvn_mesh_vertex) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
+        (totals.x > 0 && !vertices && !physicsVertices) || (totals.y > 0 && !triangles)) return LVN_ERR_CAPACITY;
+    if (totals.x && vertices) CU(cudaMemcpyAsync(vertices, ctx->d_packV.p, sizeof(lvn_mesh_vertex) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
+    if (totals.x && physicsVertices) CU(cudaMemcpyAsync(physicsVertices, ctx->d_packP.p, sizeof(float4) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
     if (totals.y) CU(cudaMemcpyAsync(triangles, ctx->d_packT.p, 12 * (size_t)totals.y, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                                     const lvn_simplify_options *unitOptions,
+                                                     lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                                     lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                                     lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                                     lvn_chunk_result *results, lvn_simplify_result *simplified)
+{
+    return generate_simplified(ctx, nChunks, chunkMinSize, unitOptions, vertices, nullptr, 0.f, vertexCapacity, triangles, triangleCapacity,
+                               seamNodes, seamCapacity, results, simplified);
+}
+
+// Clipmap::loadCollisionNodes' per-node work (clipmap.cpp:1346-1385): ConstructCollisionNodeData, then the
+// conversion Physics_UpdateWorldNodeMainMesh -> AddMeshToWorldImpl makes for Bullet (physics.cpp:549-573)
+extern "C" int lvn_meshgen_generate_collision_batch(lvn_meshgen *ctx, int nNodes, const int32_t *nodeMinSize,
+                                                    const lvn_simplify_options *unitOptions, float physicsScale,
+                                                    float *physicsVertices, lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                                    int32_t *triangles, int64_t triangleCapacity,
+                                                    lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                                    lvn_chunk_result *results, lvn_simplify_result *simplified)
+{
+    if (!physicsVertices && !vertices && vertexCapacity > 0) return LVN_ERR_INVALID_VALUE;
+    return generate_simplified(ctx, nNodes, nodeMinSize, unitOptions, vertices, physicsVertices, physicsScale, vertexCapacity,
+                               (lvn_mesh_triangle *)triangles, triangleCapacity, seamNodes, seamCapacity, results, simplified);
 }
 
 // ---------------------------------------------------------------------------

@@ -180,9 +180,11 @@ struct SimplifyMesh {
 };
 // in place, asynchronous on `st`; d_results[m] = (vertices, triangles, iterations, edges left);
 // iterations -1: a wild triangle index, -2: too large; both leave the mesh untouched.
-// With d_packV / d_packT the simplified meshes are also gathered densely in mesh order.
+// With d_packT the simplified meshes are also gathered densely in mesh order (d_packV: MeshVertex,
+// d_packP: the physics engine's vec4 = (xyz - offset) * physicsScale; either may be null).
 int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int *d_T, int4 *d_results,
-                    lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st);
+                    lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st,
+                    float4 *d_packP = nullptr, float physicsScale = 0.f);
 const char *simplify_last_error();
 
 }  // namespace lvn

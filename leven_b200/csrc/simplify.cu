@@ -709,7 +709,8 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
 __global__ void __launch_bounds__(256)
 k_pack_meshes(const SimpJobDev *__restrict__ jobsByMesh, const int4 *__restrict__ results, int numMeshes,
               const lvn_mesh_vertex *__restrict__ V, const int *__restrict__ T,
-              lvn_mesh_vertex *__restrict__ outV, int *__restrict__ outT, int2 *__restrict__ packedOffsets, int2 *__restrict__ totals)
+              lvn_mesh_vertex *__restrict__ outV, int *__restrict__ outT, int2 *__restrict__ packedOffsets, int2 *__restrict__ totals,
+              float4 *__restrict__ outP, float physicsScale)
 {
     __shared__ int s_v[8], s_t[8];
     const int m = blockIdx.x, tid = threadIdx.x;
@@ -726,7 +727,14 @@ k_pack_meshes(const SimpJobDev *__restrict__ jobsByMesh, const int4 *__restrict_
     const int4 r = results[m];
     const float4 *src = reinterpret_cast<const float4 *>(V + job.vertexOffset);
     float4 *dst = reinterpret_cast<float4 *>(outV + baseV);
-    for (int i = tid; i < r.x * 3; i += 256) dst[i] = src[i];
+    if (outV) for (int i = tid; i < r.x * 3; i += 256) dst[i] = src[i];
+    if (outP) {   // AddMeshToWorldImpl, physics.cpp:562-566: Scale_WorldToPhysics(vertex.xyz - vec4(origin, 0)), one vec4 per vertex
+        const float4 o = make_float4(job.offset[0], job.offset[1], job.offset[2], 0.f);
+        for (int i = tid; i < r.x; i += 256) {
+            const float4 x = src[i * 3];
+            outP[baseV + i] = make_float4((x.x - o.x) * physicsScale, (x.y - o.y) * physicsScale, (x.z - o.z) * physicsScale, (x.w - o.w) * physicsScale);
+        }
+    }
     const int *ts = T + (size_t)job.triangleOffset * 3;
     int *td = outT + (size_t)baseT * 3;
     for (int i = tid; i < r.y * 3; i += 256) td[i] = ts[i];
@@ -781,10 +789,12 @@ static int ensure_buffer(void **p, size_t *cap, size_t bytes)
 
 // Simplify n meshes in place in their slices of d_V / d_T, asynchronously on `st`.
 // d_results[m] (device, mesh order) = (vertices, triangles, iterations, candidate edges left).
-// With d_packV / d_packT the simplified meshes are also gathered densely, in mesh order:
+// With d_packT the simplified meshes are also gathered densely, in mesh order (vertices as MeshVertex
+// into d_packV and / or in the physics engine's format into d_packP, either may be null):
 // d_packOffsets[m] = (first vertex, first triangle), *d_packTotals = the totals.
 int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int *d_T, int4 *d_results,
-                    lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st)
+                    lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st,
+                    float4 *d_packP, float physicsScale)
 {
     if (n <= 0) return LVN_SUCCESS;
     std::vector<SimpJobDev> jd(n);
@@ -870,9 +880,10 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
         for (int k = 0; k < 9; k++) fprintf(stderr, "[simplify timing]   %-24s %9.1f %9.1f\n", names[k], t[k] / 1e3, sum[k] / 1e3 / n);
     }
 #endif
-    if (d_packV) {
+    if (d_packT) {
         MCU(cudaMemcpyAsync(B + oJobs, jd.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
-        k_pack_meshes<<<n, 256, 0, st>>>((const SimpJobDev *)(B + oJobs), d_results, n, d_V, d_T, d_packV, d_packT, d_packOffsets, d_packTotals);
+        k_pack_meshes<<<n, 256, 0, st>>>((const SimpJobDev *)(B + oJobs), d_results, n, d_V, d_T, d_packV, d_packT, d_packOffsets, d_packTotals,
+                                         d_packP, physicsScale);
         MCU(cudaGetLastError());
     }
     return LVN_SUCCESS;
@@ -916,7 +927,7 @@ extern "C" int lvn_mesh_simplify_batch(int numMeshes, const lvn_simplify_job *jo
     int4 *dRes = (int4 *)(IO + bV + bT);
     MCU(cudaMemcpyAsync(dV, vertices, sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal, cudaMemcpyHostToDevice, st));
     MCU(cudaMemcpyAsync(dT, triangles, 12 * (size_t)numTrianglesTotal, cudaMemcpyHostToDevice, st));
-    LV(simplify_device(numMeshes, meshes.data(), dV, dT, dRes, nullptr, nullptr, nullptr, nullptr, st));
+    LV(simplify_device(numMeshes, meshes.data(), dV, dT, dRes, nullptr, nullptr, nullptr, nullptr, st, nullptr, 0.f));
     std::vector<int4> res(numMeshes);
     MCU(cudaMemcpyAsync(res.data(), dRes, sizeof(int4) * numMeshes, cudaMemcpyDeviceToHost, st));
     // the simplified meshes stay in their input slots (a mesh never grows): two copies back

@@ -270,3 +270,48 @@ def test_gpu_generate_simplified_batch(lc, world, surface_cy, golden, built):
         assert rc == 0 and res4["numTriangles"].sum() == 0
     finally:
         ctx.destroy()
+
+
+@pytest.mark.gpu
+def test_gpu_collision_batch(lc, world, surface_cy, golden, built):
+    """lvn_meshgen_generate_collision_batch = Clipmap::loadCollisionNodes' per-node work: collision nodes
+    are COLLISION_NODE_SIZE = 512 on a 64-voxel context (volume_constants.h:20-21), simplified, and
+    handed to Bullet as vec4 positions relative to the node centre, scaled by PHYSICS_SCALE
+    (physics.cpp:549-573) -- against the simplified-batch route + the conversion in numpy float32,
+    and the committed digests of the reference simplifier for the two nodes the scenarios hold"""
+    rows, _ = golden
+    y1 = (surface_cy * 256 // 512) * 512
+    nodes = [[x, y, z, 512] for x in (-512, 0) for y in (y1 - 512, y1, y1 + 512) for z in (0, 512)]
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        V = np.zeros(150000, lc.MeshVertex); T = np.zeros(300000, lc.MeshTriangle); Sn = np.zeros(100000, lc.SeamNodeInfo)
+        rc, res, simp = ctx.generateSimplifiedBatch(nodes, V, T, Sn)
+        assert rc == 0
+        P = np.zeros((150000, 4), np.float32); T2 = np.zeros((300000, 3), np.int32); Sn2 = np.zeros(100000, lc.SeamNodeInfo)
+        V2 = np.zeros(150000, lc.MeshVertex)
+        rc, res2, simp2 = ctx.generateCollisionBatch(nodes, P, T2, Sn2, vertices=V2)
+        assert rc == 0, lc.last_cuda_error()
+        same = lambda a, b: all(np.array_equal(a[f], b[f]) for f in a.dtype.names if f != "seamOffset")
+        assert same(res, res2) and simp.tobytes() == simp2.tobytes()      # (a chunk's place in the seam arena is not fixed)
+        nv, nt = int(res["numVertices"].sum()), int(res["numTriangles"].sum())
+        assert nt > 20000
+        assert V[:nv].tobytes() == V2[:nv].tobytes() and np.array_equal(T["indices_"][:nt], T2[:nt])
+        for n, r, r2 in zip(nodes, res, res2):
+            assert Sn[r["seamOffset"]:r["seamOffset"] + r["numSeamNodes"]].tobytes() == Sn2[r2["seamOffset"]:r2["seamOffset"] + r2["numSeamNodes"]].tobytes()
+            origin = np.array([n[0] + 256, n[1] + 256, n[2] + 256, 0], np.float32)
+            want = (V["xyz"][r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]] - origin) * np.float32(0.05)
+            got = P[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]]
+            assert got.tobytes() == want.astype(np.float32).tobytes()
+            if r["numVertices"]:
+                assert np.all(got[:, 3] == np.float32(0.05)) and np.abs(got[:, :3]).max() <= 256 * 0.05 * 1.5
+        for name, mn in (("lod1_0", (0, y1, 0)), ("lod1_-1_1", (-512, y1, 512))):
+            r = res[nodes.index(list(mn) + [512])]
+            gv = S.as_vertices(V[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]])
+            gt = T["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]]
+            assert (str(len(gv)), str(len(gt)), sha(gv), sha(gt)) == tuple(rows[name][4:]), name
+        # physics vertices only (no MeshVertex arena): same positions and triangles
+        P3 = np.zeros((150000, 4), np.float32); T3 = np.zeros((300000, 3), np.int32)
+        rc, res3, _ = ctx.generateCollisionBatch(nodes, P3, T3, Sn2)
+        assert rc == 0 and P3.tobytes() == P.tobytes() and T3.tobytes() == T2.tobytes() and same(res3, res)
+    finally:
+        ctx.destroy()
