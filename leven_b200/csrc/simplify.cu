@@ -366,11 +366,13 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
 {
     __shared__ int s_warp[SIMP_WARPS], s_any, s_last, s_bad, s_count;
     // dynamic shared memory: [wordsE] alive-edge mask, [wordsE] its prefix, [wordsS] scratch mask, [wordsS] its
-    // prefix, then the two per-vertex arrays when they fit (ws.vtxSmem)
+    // prefix, [wordsS] + [wordsS] the same for the accepted draws, then the two per-vertex arrays when they fit
     unsigned int *s_maskE = s_dyn;
     int *s_prefE = reinterpret_cast<int *>(s_dyn + ws.wordsE);
     unsigned int *s_mask = s_dyn + 2 * ws.wordsE;
     int *s_pref = reinterpret_cast<int *>(s_mask + ws.wordsS);
+    unsigned int *s_maskA = s_mask + 2 * ws.wordsS;
+    int *s_prefA = reinterpret_cast<int *>(s_maskA + ws.wordsS);
     const SimpJobDev job = jobs[blockIdx.x];
     const lvn_simplify_options opt = job.opt;
     const int tid = threadIdx.x, NV = job.numVertices, NT0 = job.numTriangles;
@@ -387,7 +389,7 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
     //   rep     the vertex this one has been merged into (itself while it lives)
     //   vcount  triangles per vertex (FindValidCollapses' degree); between the sample and the next
     //           triangle pass the same array holds the round's collapse targets
-    int *rep = ws.vtxSmem ? reinterpret_cast<int *>(s_pref + ws.wordsS) : ws.rep + job.vtxOff;
+    int *rep = ws.vtxSmem ? s_prefA + ws.wordsS : ws.rep + job.vtxOff;
     int *vcount = ws.vtxSmem ? rep + ws.vtxSmem : ws.vcount + job.vtxOff;
     int *target = vcount;
     float4 *vx = ws.vx + job.vtxOff, *vn = ws.vn + job.vtxOff, *vc = ws.vc + job.vtxOff;
@@ -555,18 +557,17 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
             const unsigned int range = (unsigned int)NE, threshold = (0u - range) % range;
             const int K = numRandom + SIMP_SLACK;
             int *park = cand + K;
-            ballot_pass<2>(K, s_mask,
+            ballot_pass<2>(K, s_maskA,
                 [&](int k) { return ws.raw[k]; },
                 [&](int, unsigned int) { return 0; },
                 [&](int, unsigned int r, int) { return (unsigned int)((unsigned long long)r * range) >= threshold; });
             __syncthreads();
-            words_prefix(s_mask, s_pref, (K + 31) >> 5, s_warp);
-            // the cheap tests first, on every draw; the survivors are gathered so that the QEF solves
-            // below run on full warps.  (A warp reads its own mask word -- the draw's place among the
-            // accepted ones -- before it overwrites that word with the survivors' mask.)
+            words_prefix(s_maskA, s_prefA, (K + 31) >> 5, s_warp);
+            // the cheap tests first, on every draw (its place among the accepted ones from the first pair of
+            // word arrays); the survivors are gathered so that the QEF solves below run on full warps
             ballot_pass<2>(K, s_mask,
                 [&](int k) {
-                    const int rank = compact_slot(s_mask, s_pref, k);
+                    const int rank = compact_slot(s_maskA, s_prefA, k);
                     const int i = (int)(((unsigned long long)ws.raw[k] * range) >> 32);
                     const int j = select_bit(s_maskE, s_prefE, wordsE, i);        // the i-th alive edge
                     const uint2 e = edges[j];
@@ -814,7 +815,7 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
         const double draws = (double)j.numTriangles * 3.0 * (double)j.opt.edgeFraction + SIMP_SLACK;
         const double other = std::max(draws, (double)j.numVertices);
         // shared memory: mask + prefix words over the raw edges, and over the draws / the vertices
-        if (((double)j.numTriangles * 3.0 / 32.0 + other / 32.0 + 128.0) * 8.0 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // iterations = -2
+        if (((double)j.numTriangles * 3.0 / 32.0 + 2.0 * other / 32.0 + 192.0) * 8.0 > (double)SIMP_MAX_SMEM) { d.skip = 1; continue; }   // iterations = -2
         maxEdges = std::max(maxEdges, j.numTriangles * 3);
         maxOther = std::max(maxOther, (int)other);
         maxDraws = std::max(maxDraws, (int)draws);
@@ -827,8 +828,8 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     LV(ensure_raw(maxDraws));
     const int wordsE = ((maxEdges + 31) / 32 + 31) & ~31, wordsS = ((maxOther + 31) / 32 + 31) & ~31;
     int vtxSmem = (maxVerts + 31) & ~31;
-    if (((size_t)wordsE + wordsS + vtxSmem) * 8 > SIMP_MAX_SMEM) vtxSmem = 0;     // per-vertex arrays fall back to global memory
-    const size_t smem = ((size_t)wordsE + wordsS + vtxSmem) * 8;
+    if (((size_t)wordsE + 2 * (size_t)wordsS + vtxSmem) * 8 > SIMP_MAX_SMEM) vtxSmem = 0;     // per-vertex arrays fall back to global memory
+    const size_t smem = ((size_t)wordsE + 2 * (size_t)wordsS + vtxSmem) * 8;
     if (smem > 48 * 1024 && smem > g_simp.smemSet) {
         MCU(cudaFuncSetAttribute(k_simplify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMP_MAX_SMEM));
         g_simp.smemSet = SIMP_MAX_SMEM;
