@@ -27,6 +27,7 @@
 // Vertices come out in the reference's order (bit-identical arrays); triangles are the same set of
 // index triples with the same winding, in (owner vertex, edge) order instead of recursion order.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -34,9 +35,15 @@
 
 namespace lvn {
 
-constexpr int SEAM_BLOCK = 256;
+constexpr int SEAM_BLOCK = 1024;      // one block per seam; the launch lasts as long as its largest seam, so a seam gets a whole SM
 constexpr unsigned int SEAM_INTERNAL = 0xfffffffeu;
 constexpr unsigned int SEAM_NONE = 0xffffffffu;
+// A seam of the default terrain has a few hundred leaves: its cell table, its sort keys and its
+// quad flags fit the block's shared memory, and only larger seams use the global scratch slices.
+constexpr int SEAM_SMEM_TABLE = 4096;        // entries (8 B key + 4 B value); used while leaves * levels <= 3/4 of it
+constexpr int SEAM_SMEM_KEYS = SEAM_SMEM_TABLE;   // selected leaves whose sort keys fit (they lie where the table's keys will)
+constexpr int SEAM_SMEM_WORDS = 1024;        // quad flag words: 2730 leaves * 12 edges / 32
+constexpr size_t SEAM_SMEM_BYTES = (size_t)SEAM_SMEM_TABLE * 12 + (size_t)SEAM_SMEM_WORDS * 16;
 
 struct SeamJobDev {
     int hostMin[3], hostSize;
@@ -131,13 +138,52 @@ __device__ __forceinline__ bool seam_same_chunk(int3 a, int3 b)
     return (a.x >> 6) == (b.x >> 6) && (a.y >> 6) == (b.y >> 6) && (a.z >> 6) == (b.z >> 6);
 }
 
+// exclusive prefix of the popcounts of flags[0 .. nwords) into pref; returns the total (same in every thread)
+__device__ __forceinline__ int seam_words_prefix(const unsigned int *flags, int *pref, int nwords, int *s_warp)
+{
+    const int tid = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < nwords; base += SEAM_BLOCK) {
+        const int w = base + tid;
+        const int c = w < nwords ? __popc(flags[w]) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int q = 0; q < SEAM_BLOCK / 32; q++) { const int v = s_warp[q]; if (q < (tid >> 5)) woff += v; tot += v; }
+        if (w < nwords) pref[w] = carry + woff + incl - c;
+        carry += tot;
+        __syncthreads();
+    }
+    return carry;
+}
+
+#ifdef LVN_SEAM_TIMING
+__device__ long long g_seamTiming[16];      // [0..8) sums over blocks, [8..16) maxima
+#define SPHASE(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd((unsigned long long *)&g_seamTiming[k], (unsigned long long)(now_ - t_)); atomicMax(&g_seamTiming[8 + (k)], now_ - t_); t_ = now_; } } while (0)
+#else
+#define SPHASE(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(SEAM_BLOCK)
-k_seam(const SeamJobDev *__restrict__ jobs, const lvn_seam_neighbour *__restrict__ neighbours,
+k_seam(const SeamJobDev *__restrict__ jobs, const int *__restrict__ launchOrder, const lvn_seam_neighbour *__restrict__ neighbours,
        const lvn_seam_node_info *__restrict__ nodes, int voxelsPerChunk, SeamScratch ws,
        lvn_mesh_vertex *__restrict__ vertices, int *__restrict__ triangles, int4 *__restrict__ results)
 {
-    __shared__ int s_n, s_total, s_warp[SEAM_BLOCK / 32], s_run;
-    const SeamJobDev job = jobs[blockIdx.x];
+    __shared__ int s_n, s_total, s_warp[SEAM_BLOCK / 32];
+    extern __shared__ unsigned long long s_seam[];
+    unsigned long long *s_tkeys = s_seam;                                             // [SEAM_SMEM_TABLE]
+    unsigned long long *s_keys = s_seam;                                              // [SEAM_SMEM_KEYS]: phase 2 only
+    unsigned int *s_tvals = reinterpret_cast<unsigned int *>(s_seam + SEAM_SMEM_TABLE);  // [SEAM_SMEM_TABLE]
+    unsigned int *s_flags = s_tvals + SEAM_SMEM_TABLE;                                // [SEAM_SMEM_WORDS]
+    int *s_fpref = reinterpret_cast<int *>(s_flags + SEAM_SMEM_WORDS);                // [SEAM_SMEM_WORDS]
+    unsigned int *s_flagsB = s_flags + 2 * SEAM_SMEM_WORDS;                           // the same pair for the quads
+    int *s_fprefB = reinterpret_cast<int *>(s_flags + 3 * SEAM_SMEM_WORDS);
+    const int jobIndex = launchOrder[blockIdx.x];     // largest seams first
+    const SeamJobDev job = jobs[jobIndex];
     const int tid = threadIdx.x;
     int4 *leaf = ws.leaf + job.firstCandidate;
     unsigned long long *key = ws.key + job.firstCandidate;
@@ -145,12 +191,11 @@ k_seam(const SeamJobDev *__restrict__ jobs, const lvn_seam_neighbour *__restrict
     int4 *sorted = ws.sorted + job.firstCandidate;
     int *quadCount = ws.quadCount + job.firstCandidate;
     int4 *quads = ws.quads + (size_t)job.firstCandidate * 12;
-    unsigned long long *tkeys = ws.tableKeys + job.tableOffset;
-    unsigned int *tvals = ws.tableVals + job.tableOffset;
-    const unsigned int tmask = job.tableMask;
-    if (tid == 0) { s_n = 0; s_total = 0; s_run = 0; }
-    for (unsigned int i = tid; i <= tmask; i += SEAM_BLOCK) tkeys[i] = 0ull;
+    if (tid == 0) { s_n = 0; s_total = 0; }
     __syncthreads();
+#ifdef LVN_SEAM_TIMING
+    long long t_ = clock64();
+#endif
 
     // ---- 1. select (SelectSeamNodes, clipmap.cpp:542-569) ----
     {
@@ -180,37 +225,89 @@ k_seam(const SeamJobDev *__restrict__ jobs, const lvn_seam_neighbour *__restrict
     }
     __syncthreads();
     const int nSel = s_n;
+    SPHASE(0);
 
     // ---- 2. DFS order by counting + vertices (GenerateVertexIndices, octree.cpp:196-233) ----
     // A coarser neighbour is returned for several of the host's slots (findActiveNodes,
     // clipmap.cpp:1449-1481) and its nodes can pass the filter of more than one: the reference
     // then links the same leaf twice, which changes nothing.  Keep the first of equal keys.
-    for (int i = tid; i < nSel; i += SEAM_BLOCK) {
-        const unsigned long long ki = key[i];
-        int first = 1;
-        for (int j = 0; j < i; j++) first &= key[j] != ki;
-        quadCount[i] = first;
-        if (first) atomicAdd(&s_total, 1);
-    }
-    __syncthreads();
-    const int n = s_total;
-    for (int i = tid; i < nSel; i += SEAM_BLOCK) {
-        if (!quadCount[i]) continue;
-        const unsigned long long ki = key[i];
-        int rank = 0;
-        for (int j = 0; j < nSel; j++) rank += (key[j] < ki) & quadCount[j];
-        sorted[rank] = leaf[i];
-        if (rank < job.vertexCap) {
-            const lvn_seam_node_info nd = nodes[src[i]];
-            float4 *vp = reinterpret_cast<float4 *>(&vertices[job.vertexBase + rank]);
-            vp[0] = make_float4(nd.position[0], nd.position[1], nd.position[2], 0.f);
-            vp[1] = make_float4(nd.normal[0], nd.normal[1], nd.normal[2], 0.f);
-            vp[2] = make_float4(job.colour[0], job.colour[1], job.colour[2], (float)(nd.localspaceMin[3] >> 8));
+    // Up to SEAM_SMEM_KEYS leaves: a bitonic sort of (key << 16 | selection index) in shared memory; the
+    // first of a run of equal keys is then the earliest selected, and a leaf's rank the number of run
+    // heads before it.  Larger seams rank by counting through the global scratch.
+    int n;
+    if (nSel <= SEAM_SMEM_KEYS) {
+        int P = 32;
+        while (P < nSel) P <<= 1;
+        for (int i = tid; i < P; i += SEAM_BLOCK) s_keys[i] = i < nSel ? ((key[i] << 16) | (unsigned long long)i) : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < P; i += SEAM_BLOCK) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long a = s_keys[i], b = s_keys[l];
+                        if (((i & k) == 0) ? (a > b) : (a < b)) { s_keys[i] = b; s_keys[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int p = tid; p < P; p += SEAM_BLOCK) {      // run heads as ballot words (P is a multiple of 32)
+            const bool head = p < nSel && (p == 0 || (s_keys[p - 1] >> 16) != (s_keys[p] >> 16));
+            const unsigned int m = __ballot_sync(0xffffffffu, head);
+            if ((tid & 31) == 0) s_flags[p >> 5] = m;
         }
+        __syncthreads();
+        n = seam_words_prefix(s_flags, s_fpref, P >> 5, s_warp);
+        for (int p = tid; p < nSel; p += SEAM_BLOCK) {
+            const unsigned int m = s_flags[p >> 5], bit = 1u << (p & 31);
+            if (!(m & bit)) continue;
+            const int rank = s_fpref[p >> 5] + __popc(m & (bit - 1u));
+            const int i = (int)(s_keys[p] & 0xffffull);
+            sorted[rank] = leaf[i];
+            if (rank < job.vertexCap) {
+                const lvn_seam_node_info nd = nodes[src[i]];
+                float4 *vp = reinterpret_cast<float4 *>(&vertices[job.vertexBase + rank]);
+                vp[0] = make_float4(nd.position[0], nd.position[1], nd.position[2], 0.f);
+                vp[1] = make_float4(nd.normal[0], nd.normal[1], nd.normal[2], 0.f);
+                vp[2] = make_float4(job.colour[0], job.colour[1], job.colour[2], (float)(nd.localspaceMin[3] >> 8));
+            }
+        }
+        __syncthreads();
+    } else {
+        for (int i = tid; i < nSel; i += SEAM_BLOCK) {
+            const unsigned long long ki = key[i];
+            int first = 1;
+            for (int j = 0; j < i; j++) first &= key[j] != ki;
+            quadCount[i] = first;
+            if (first) atomicAdd(&s_total, 1);
+        }
+        __syncthreads();
+        n = s_total;
+        for (int i = tid; i < nSel; i += SEAM_BLOCK) {
+            if (!quadCount[i]) continue;
+            const unsigned long long ki = key[i];
+            int rank = 0;
+            for (int j = 0; j < nSel; j++) rank += (key[j] < ki) & quadCount[j];
+            sorted[rank] = leaf[i];
+            if (rank < job.vertexCap) {
+                const lvn_seam_node_info nd = nodes[src[i]];
+                float4 *vp = reinterpret_cast<float4 *>(&vertices[job.vertexBase + rank]);
+                vp[0] = make_float4(nd.position[0], nd.position[1], nd.position[2], 0.f);
+                vp[1] = make_float4(nd.normal[0], nd.normal[1], nd.normal[2], 0.f);
+                vp[2] = make_float4(job.colour[0], job.colour[1], job.colour[2], (float)(nd.localspaceMin[3] >> 8));
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
+    SPHASE(1);
     // ---- 3. leaves and all their ancestors into the table (Octree_ConstructUpwards) ----
+    const bool tableInSmem = (long long)n * (job.rootLog2 + 1) * 4 <= (long long)SEAM_SMEM_TABLE * 3;
+    unsigned long long *tkeys = tableInSmem ? s_tkeys : ws.tableKeys + job.tableOffset;
+    unsigned int *tvals = tableInSmem ? s_tvals : ws.tableVals + job.tableOffset;
+    const unsigned int tmask = tableInSmem ? (unsigned int)(SEAM_SMEM_TABLE - 1) : job.tableMask;
+    for (unsigned int i = tid; i <= tmask; i += SEAM_BLOCK) tkeys[i] = 0ull;
+    __syncthreads();
     for (int i = tid; i < n; i += SEAM_BLOCK) {
         const int4 L = sorted[i];
         const int lg = L.w & 0xff;
@@ -223,10 +320,44 @@ k_seam(const SeamJobDev *__restrict__ jobs, const lvn_seam_neighbour *__restrict
     __syncthreads();
 
     // ---- 4. contour: every (leaf, edge) ----
+    SPHASE(2);
+    // ---- 4. contour.  Of a leaf's 12 edges only those with a sign change inside the root can yield a
+    //      quad: that cheap test runs on every (leaf, edge) item, the survivors are numbered by ballot
+    //      words + prefix, and the table walks below run on full warps of survivors, each finding its
+    //      item by a select over the words.  Which survivors yield a quad is a second set of words. ----
     const int rootUnits = 1 << job.rootLog2;
-    for (int item = tid; item < n * 12; item += SEAM_BLOCK) {
+    const int nItems = n * 12, nWords = (nItems + 31) >> 5;
+    const bool flagsInSmem = nWords <= SEAM_SMEM_WORDS;
+    unsigned int *flagsA = flagsInSmem ? s_flags : reinterpret_cast<unsigned int *>(quadCount);
+    int *prefA = flagsInSmem ? s_fpref : src;
+    unsigned int *flagsB = flagsInSmem ? s_flagsB : reinterpret_cast<unsigned int *>(key);
+    int *prefB = flagsInSmem ? s_fprefB : reinterpret_cast<int *>(key) + job.numCandidates;
+    for (int item = tid; item < nWords * 32; item += SEAM_BLOCK) {
+        bool cand = false;
+        if (item < nItems) {
+            const int r = item / 12, e = item - r * 12;
+            const int4 L = sorted[r];
+            const int s = 1 << (L.w & 0xff), corners = (L.w >> 8) & 0xff, dir = e >> 2;
+            const int own = dir == 0 ? 3 - e : (dir == 1 ? (e == 7 ? 0 : (e == 5 ? 1 : (e == 6 ? 2 : 3))) : 11 - e);
+            const int mp = dir == 0 ? L.y : (dir == 1 ? L.z : L.x), mq = dir == 0 ? L.z : (dir == 1 ? L.x : L.y);
+            const int lp = mp + (((own >> 1) & 1) ? 0 : s), lq = mq + ((own & 1) ? 0 : s);
+            const int c0 = dir == 0 ? (e & 3) : (dir == 1 ? ((e & 1) | ((e & 2) << 1)) : ((e & 3) << 1));
+            const int c1 = c0 | (dir == 0 ? 4 : (dir == 1 ? 2 : 1));
+            cand = (((corners >> c0) ^ (corners >> c1)) & 1) && lp > 0 && lq > 0 && lp < rootUnits && lq < rootUnits;
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, cand);
+        if ((tid & 31) == 0) flagsA[item >> 5] = m;
+    }
+    __syncthreads();
+    const int nLive = seam_words_prefix(flagsA, prefA, nWords, s_warp);
+    const int nWordsB = (nLive + 31) >> 5;
+    for (int d = tid; d < nWordsB * 32; d += SEAM_BLOCK) {
+        bool ok = d < nLive;
+        if (ok) {
+        int lo = 0, hi = nWords - 1;            // the d-th survivor: its word by binary search over the prefix, its bit by fns
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (prefA[mid] <= d) lo = mid; else hi = mid - 1; }
+        const int item = (lo << 5) + (int)__fns(flagsA[lo], 0, d - prefA[lo] + 1);
         const int r = item / 12, e = item - r * 12;
-        int4 q = make_int4(-1, -1, -1, -1);
         const int4 L = sorted[r];
         const int lg = L.w & 0xff, s = 1 << lg, corners = (L.w >> 8) & 0xff;
         const int dir = e >> 2;
@@ -242,8 +373,7 @@ k_seam(const SeamJobDev *__restrict__ jobs, const lvn_seam_neighbour *__restrict
         // sign change and winding come from this leaf (the first minimal node)
         const int c0 = dir == 0 ? (e & 3) : (dir == 1 ? ((e & 1) | ((e & 2) << 1)) : ((e & 3) << 1));   // edgevmap[e][0]
         const int c1 = c0 | (dir == 0 ? 4 : (dir == 1 ? 2 : 1));
-        const int m0 = (corners >> c0) & 1, m1 = (corners >> c1) & 1;
-        bool ok = m0 != m1 && line[p] > 0 && line[qa] > 0 && line[p] < rootUnits && line[qa] < rootUnits;
+        const int m1 = (corners >> c1) & 1;
         int4 Lq[4];
         int idx[4], pt[4][3];
         for (int i = 0; i < 4 && ok; i++) {
@@ -290,47 +420,31 @@ k_seam(const SeamJobDev *__restrict__ jobs, const lvn_seam_neighbour *__restrict
                 if (all) ok = false;
             }
         }
-        if (ok) q = make_int4(idx[0], idx[1], idx[2], idx[3] | ((m1 != 1) ? (1 << 30) : 0));   // flip = m1 != 1
-        quads[item] = q;
+        if (ok) quads[d] = make_int4(idx[0], idx[1], idx[2], idx[3] | ((m1 != 1) ? (1 << 30) : 0));   // flip = m1 != 1
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        if ((tid & 31) == 0) flagsB[d >> 5] = m;
     }
     __syncthreads();
 
-    // ---- 5. emit: per-leaf counts, block scan, triangles (ContourProcessEdge, octree.cpp:270-283) ----
-    for (int base = 0; base < n; base += SEAM_BLOCK) {
-        const int r = base + tid;
-        int cnt = 0;
-        if (r < n)
-            for (int e = 0; e < 12; e++) cnt += quads[r * 12 + e].x >= 0;
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
-        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-        __syncthreads();
-        int woff = 0;
-        for (int w = 0; w < (tid >> 5); w++) woff += s_warp[w];
-        int off = s_run + woff + incl - cnt;
-        if (r < n) {
-            quadCount[r] = cnt;
-            for (int e = 0; e < 12; e++) {
-                const int4 q = quads[r * 12 + e];
-                if (q.x < 0) continue;
-                if (2 * off + 2 <= job.triangleCap) {
-                    const int i0 = q.x, i1 = q.y, i2 = q.z, i3 = q.w & ~(1 << 30);
-                    int *t = triangles + ((size_t)job.triangleBase + 2 * (size_t)off) * 3;
-                    if (!(q.w & (1 << 30))) { t[0] = i0; t[1] = i1; t[2] = i3; t[3] = i0; t[4] = i3; t[5] = i2; }
-                    else                    { t[0] = i0; t[1] = i3; t[2] = i1; t[3] = i0; t[4] = i2; t[5] = i3; }
-                }
-                off++;
-            }
-        }
-        __syncthreads();
-        if (tid == SEAM_BLOCK - 1) s_run += woff + incl;
-        __syncthreads();
+    SPHASE(3);
+    // ---- 5. emit: triangles in (leaf, edge) order (ContourProcessEdge, octree.cpp:270-283) ----
+    const int quadsTotal = seam_words_prefix(flagsB, prefB, nWordsB, s_warp);
+    for (int d = tid; d < nLive; d += SEAM_BLOCK) {
+        const unsigned int m = flagsB[d >> 5], bit = 1u << (d & 31);
+        if (!(m & bit)) continue;
+        const int off = prefB[d >> 5] + __popc(m & (bit - 1u));
+        if (2 * off + 2 > job.triangleCap) continue;
+        const int4 q = quads[d];
+        const int i0 = q.x, i1 = q.y, i2 = q.z, i3 = q.w & ~(1 << 30);
+        int *t = triangles + ((size_t)job.triangleBase + 2 * (size_t)off) * 3;
+        if (!(q.w & (1 << 30))) { t[0] = i0; t[1] = i1; t[2] = i3; t[3] = i0; t[4] = i3; t[5] = i2; }
+        else                    { t[0] = i0; t[1] = i3; t[2] = i1; t[3] = i0; t[4] = i2; t[5] = i3; }
     }
+    SPHASE(4);
     if (tid == 0) {
-        const int quadsTotal = s_run;
         // Octree_GenerateMesh returns no mesh at all when there is no triangle (octree.cpp:536-540)
-        results[blockIdx.x] = make_int4(quadsTotal > 0 ? n : 0, 2 * quadsTotal, n, (n > job.vertexCap || 2 * quadsTotal > job.triangleCap) ? 1 : 0);
+        results[jobIndex] = make_int4(quadsTotal > 0 ? n : 0, 2 * quadsTotal, n, (n > job.vertexCap || 2 * quadsTotal > job.triangleCap) ? 1 : 0);
     }
 }
 
@@ -426,7 +540,7 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
                  oQuads = take(sizeof(int4) * 12 * candPad), oTK = take(8 * std::max<size_t>(totalTable, 1)),
                  oTV = take(4 * std::max<size_t>(totalTable, 1)), oV = take(sizeof(lvn_mesh_vertex) * candPad),
                  oT = take(sizeof(int) * 3 * 8 * candPad), oRes = take(sizeof(int4) * numSeams),
-                 oPack = take(sizeof(int4) * numSeams), oPV = take(sizeof(lvn_mesh_vertex) * candPad), oPT = take(sizeof(int) * 3 * 8 * candPad);
+                 oPack = take(sizeof(int4) * numSeams), oOrder = take(sizeof(int) * numSeams), oPV = take(sizeof(lvn_mesh_vertex) * candPad), oPT = take(sizeof(int) * 3 * 8 * candPad);
     if (off > g_seam.blobCap) {
         if (g_seam.d_blob) SCU(cudaFree(g_seam.d_blob));
         g_seam.d_blob = nullptr; g_seam.blobCap = 0;
@@ -436,16 +550,36 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
     char *B = (char *)g_seam.d_blob;
     cudaStream_t st = g_seam.stream;
     SCU(cudaMemcpyAsync(B + oJobs, jd.data(), sizeof(SeamJobDev) * numSeams, cudaMemcpyHostToDevice, st));
+    std::vector<int> order(numSeams);
+    for (int i = 0; i < numSeams; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jd[a].numCandidates > jd[b].numCandidates; });
+    SCU(cudaMemcpyAsync(B + oOrder, order.data(), sizeof(int) * numSeams, cudaMemcpyHostToDevice, st));
     if (numNeighbours) SCU(cudaMemcpyAsync(B + oNb, neighbours, sizeof(lvn_seam_neighbour) * numNeighbours, cudaMemcpyHostToDevice, st));
-    if (numSeamNodes) SCU(cudaMemcpyAsync(B + oNodes, seamNodes, sizeof(lvn_seam_node_info) * numSeamNodes, cudaMemcpyHostToDevice, st));
+    // (cudaMemcpyDefault: the seam nodes may also be the device arena of a batch view)
+    if (numSeamNodes) SCU(cudaMemcpyAsync(B + oNodes, seamNodes, sizeof(lvn_seam_node_info) * numSeamNodes, cudaMemcpyDefault, st));
     SeamScratch ws;
     ws.leaf = (int4 *)(B + oLeaf); ws.key = (unsigned long long *)(B + oKey); ws.src = (int *)(B + oSrc);
     ws.sorted = (int4 *)(B + oSorted); ws.quadCount = (int *)(B + oCnt); ws.quads = (int4 *)(B + oQuads);
     ws.tableKeys = (unsigned long long *)(B + oTK); ws.tableVals = (unsigned int *)(B + oTV);
-    k_seam<<<numSeams, SEAM_BLOCK, 0, st>>>((const SeamJobDev *)(B + oJobs), (const lvn_seam_neighbour *)(B + oNb),
+    static bool smemSet = false;
+    if (!smemSet) { SCU(cudaFuncSetAttribute(k_seam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEAM_SMEM_BYTES)); smemSet = true; }
+    k_seam<<<numSeams, SEAM_BLOCK, SEAM_SMEM_BYTES, st>>>((const SeamJobDev *)(B + oJobs), (const int *)(B + oOrder), (const lvn_seam_neighbour *)(B + oNb),
                                             (const lvn_seam_node_info *)(B + oNodes), voxelsPerChunk, ws,
                                             (lvn_mesh_vertex *)(B + oV), (int *)(B + oT), (int4 *)(B + oRes));
     SCU(cudaGetLastError());
+#ifdef LVN_SEAM_TIMING
+    {
+        long long t[16];
+        SCU(cudaStreamSynchronize(st));
+        SCU(cudaMemcpyFromSymbol(t, g_seamTiming, sizeof(t)));
+        fprintf(stderr, "[seam timing] %d seams, kilocycles summed over blocks: select %.0f  order %.0f  table %.0f  contour %.0f  emit %.0f\n",
+                numSeams, t[0] / 1e3, t[1] / 1e3, t[2] / 1e3, t[3] / 1e3, t[4] / 1e3);
+        fprintf(stderr, "[seam timing]           slowest block of each phase:   select %.0f  order %.0f  table %.0f  contour %.0f  emit %.0f\n",
+                t[8] / 1e3, t[9] / 1e3, t[10] / 1e3, t[11] / 1e3, t[12] / 1e3);
+        memset(t, 0, sizeof(t));
+        SCU(cudaMemcpyToSymbol(g_seamTiming, t, sizeof(t)));
+    }
+#endif
     std::vector<int4> res(numSeams);
     SCU(cudaMemcpyAsync(res.data(), B + oRes, sizeof(int4) * numSeams, cudaMemcpyDeviceToHost, st));
     SCU(cudaStreamSynchronize(st));

@@ -37,6 +37,7 @@ for _ in range(n):
     rc, _, _, sres = lc.GenerateClipmapSeamMeshesPacked(64, pj, pn, pa, Vb, Tb)
 gpu_s = (time.perf_counter() - t0) / n
 out = {"seams": len(jobs), "candidate_nodes": cand, "uploaded_nodes": int(len(pa)), "selected_nodes": int(sres["numSelectedNodes"].sum()),
+       "selected_nodes_max": int(sres["numSelectedNodes"].max()), "candidate_nodes_max": int(max(pn["numNodes"][j["firstNeighbour"]:j["firstNeighbour"] + j["numNeighbours"]].sum() for j in pj)),
        "vertices": int(sres["numVertices"].sum()), "triangles": int(sres["numTriangles"].sum()),
        "gpu_ms_per_batch": gpu_s * 1e3, "gpu_seams_per_s": len(jobs) / gpu_s,
        "gpu_what": "one lvn_seam_mesh_generate_batch call: H2D of the seam nodes (pageable), one kernel, D2H of the meshes"}
