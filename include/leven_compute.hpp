@@ -150,4 +150,29 @@ private:
 // compute.h:81
 inline const char* GetCLErrorString(int error) { return lvn_error_string(error); }
 
+// ng_mesh_simplify.h:6-36: the simplifier clipmap.cpp runs on every exported mesh (clipmap.cpp:449-465,495-501)
+struct MeshSimplificationOptions
+{
+    float edgeFraction = 0.125f;
+    int maxIterations = 10;
+    float targetPercentage = 0.05f;
+    float maxError = 5.f;
+    float maxEdgeSize = 2.5f;
+    float minAngleCosine = 0.8f;
+};
+
+inline void ngMeshSimplifier(MeshBuffer* mesh, const lvn_shim::vec4& worldSpaceOffset, const MeshSimplificationOptions& options)
+{
+    lvn_simplify_job job = { 0, mesh->numVertices, 0, mesh->numTriangles,
+                             { worldSpaceOffset.x, worldSpaceOffset.y, worldSpaceOffset.z, worldSpaceOffset.w } };
+    const lvn_simplify_options opt = { options.edgeFraction, options.maxIterations, options.targetPercentage,
+                                       options.maxError, options.maxEdgeSize, options.minAngleCosine };
+    lvn_simplify_result r = { mesh->numVertices, mesh->numTriangles, 0, 0 };
+    if (lvn_mesh_simplify_batch(1, &job, &opt, 1, reinterpret_cast<lvn_mesh_vertex*>(mesh->vertices), mesh->numVertices,
+                                reinterpret_cast<lvn_mesh_triangle*>(mesh->triangles), mesh->numTriangles, &r) < 0)
+        return;                                   // the mesh is left as it was (the reference returns void)
+    mesh->numVertices = r.numVertices;
+    mesh->numTriangles = r.numTriangles;
+}
+
 #endif  // LEVEN_COMPUTE_HPP

@@ -2,6 +2,7 @@
 include/leven_compute.h declares, and the POD layouts are the reference's."""
 import ctypes as C
 import os
+import sys
 import re
 import subprocess
 import tempfile
@@ -80,6 +81,9 @@ int main() {
   static_assert(sizeof(MeshTriangle) == 12, "MeshTriangle");
   Compute_MeshGenContext* (*create)(const int) = &Compute_MeshGenContext::create;
   (void)create;
+  void (*simplify)(MeshBuffer*, const lvn_shim::vec4&, const MeshSimplificationOptions&) = &ngMeshSimplifier;   // ng_mesh_simplify.h:32-36
+  (void)simplify;
+  static_assert(sizeof(lvn_simplify_options) == 24 && sizeof(lvn_simplify_job) == 32 && sizeof(lvn_clipmap_node) == 24, "simplify / update PODs");
   return GetCLErrorString(0) == nullptr;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -98,6 +102,14 @@ def test_no_device_fails_loudly(built):
     assert lc.Compute_MeshGenContext.create(64).privateCtx_ is None
     assert lc.GetCLErrorString(lc.LVN_ERR_NO_DEVICE) == "LVN_ERR_NO_DEVICE"
     assert lc.FindNextPrime(2048) == 2053        # host-only helper works anywhere
+    # the widened rows likewise: no device, no result
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import simplify_scenarios as S
+    v, t = S.torus()
+    rc, out, res = lc.ngMeshSimplifierBatch([(v, t, [0, 0, 0])], lc.SimplifyOptions.make())
+    assert rc == lc.LVN_ERR_NO_DEVICE and len(out[0][1]) == 0
+    assert lc.GenerateClipmapSeamMeshes(64, [([0, 0, 0], 256, [])])[0] == lc.LVN_ERR_NO_DEVICE
 
 
 def test_packed_fp32_is_not_contracted(built):
