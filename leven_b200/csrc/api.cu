@@ -1139,12 +1139,14 @@ extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const i
 // generateChunkMesh, then ngMeshSimplifier with the options the clipmap derives from the node size.
 // The meshes stay in HBM between the two; only the simplified meshes cross PCIe -- as MeshVertex
 // (`vertices`) and / or in the physics engine's format (`physicsVertices`, AddMeshToWorldImpl).
-static int generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
-                               const lvn_simplify_options *unitOptions,
-                               lvn_mesh_vertex *vertices, float *physicsVertices, float physicsScale, int64_t vertexCapacity,
-                               lvn_mesh_triangle *triangles, int64_t triangleCapacity,
-                               lvn_seam_node_info *seamNodes, int64_t seamCapacity,
-                               lvn_chunk_result *results, lvn_simplify_result *simplified)
+// deferMeshCopies: return once the two mesh copies are queued (results, counts and seam nodes are
+// final by then); the caller overlaps other work and calls lvn::meshgen_wait before reading the meshes.
+int lvn::generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                             const lvn_simplify_options *unitOptions,
+                             lvn_mesh_vertex *vertices, float *physicsVertices, float physicsScale, int64_t vertexCapacity,
+                             lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                             lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                             lvn_chunk_result *results, lvn_simplify_result *simplified, bool deferMeshCopies)
 {
     if (!results || !unitOptions) return LVN_ERR_INVALID_VALUE;
     BatchOpts opts;
@@ -1223,7 +1225,14 @@ static int generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chu
     if (totals.x && vertices) CU(cudaMemcpyAsync(vertices, ctx->d_packV.p, sizeof(lvn_mesh_vertex) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
     if (totals.x && physicsVertices) CU(cudaMemcpyAsync(physicsVertices, ctx->d_packP.p, sizeof(float4) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
     if (totals.y) CU(cudaMemcpyAsync(triangles, ctx->d_packT.p, 12 * (size_t)totals.y, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (!deferMeshCopies) CU(cudaStreamSynchronize(st));
+    return LVN_SUCCESS;
+}
+
+int lvn::meshgen_wait(lvn_meshgen *ctx)
+{
+    if (!ctx) return LVN_ERR_INVALID_VALUE;
+    CU(cudaStreamSynchronize(ctx->stream));
     return LVN_SUCCESS;
 }
 
@@ -1235,7 +1244,7 @@ extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChun
                                                      lvn_chunk_result *results, lvn_simplify_result *simplified)
 {
     return generate_simplified(ctx, nChunks, chunkMinSize, unitOptions, vertices, nullptr, 0.f, vertexCapacity, triangles, triangleCapacity,
-                               seamNodes, seamCapacity, results, simplified);
+                               seamNodes, seamCapacity, results, simplified, false);
 }
 
 // Clipmap::loadCollisionNodes' per-node work (clipmap.cpp:1346-1385): ConstructCollisionNodeData, then the
@@ -1249,7 +1258,7 @@ extern "C" int lvn_meshgen_generate_collision_batch(lvn_meshgen *ctx, int nNodes
 {
     if (!physicsVertices && !vertices && vertexCapacity > 0) return LVN_ERR_INVALID_VALUE;
     return generate_simplified(ctx, nNodes, nodeMinSize, unitOptions, vertices, physicsVertices, physicsScale, vertexCapacity,
-                               (lvn_mesh_triangle *)triangles, triangleCapacity, seamNodes, seamCapacity, results, simplified);
+                               (lvn_mesh_triangle *)triangles, triangleCapacity, seamNodes, seamCapacity, results, simplified, false);
 }
 
 // ---------------------------------------------------------------------------

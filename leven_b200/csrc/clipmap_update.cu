@@ -103,9 +103,10 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
             memcpy(&minSize[4 * (size_t)i], construct[i].min, 3 * sizeof(int32_t));
             minSize[4 * (size_t)i + 3] = construct[i].size;
         }
-        const int rc = lvn_meshgen_generate_simplified_batch(ctx, numConstruct, minSize.data(), unitOptions, vertices, vertexCapacity,
-                                                             triangles, triangleCapacity, seamNodes ? seamNodes + seamNodesUsed : nullptr,
-                                                             seamCapacity - seamNodesUsed, constructResults, nullptr);
+        // (the node meshes are still on their way to the host arenas while pass 2 runs: it needs the seam nodes only)
+        const int rc = lvn::generate_simplified(ctx, numConstruct, minSize.data(), unitOptions, vertices, nullptr, 0.f, vertexCapacity,
+                                                triangles, triangleCapacity, seamNodes ? seamNodes + seamNodesUsed : nullptr,
+                                                seamCapacity - seamNodesUsed, constructResults, nullptr, true);
         int64_t sn = 0;
         for (int i = 0; i < numConstruct; i++) {
             const lvn_chunk_result &r = constructResults[i];
@@ -146,7 +147,7 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
     std::vector<int> updates;
     for (int i = 0; i < numActive + numConstruct; i++) if (marked[i]) updates.push_back(i);   // (the reference iterates an unordered_set)
     totals->numSeamUpdates = (int32_t)updates.size();
-    if (updates.empty()) return LVN_SUCCESS;
+    if (updates.empty()) return lvn::meshgen_wait(ctx);
 
     // ---- 3. GenerateClipmapSeamMesh for the whole set (clipmap.cpp:573-611) ----
     std::vector<lvn_seam_job> jobs(updates.size());
@@ -191,5 +192,6 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
         r.vertexOffset += (int32_t)totals->nodeVertices;
         r.triangleOffset += (int32_t)totals->nodeTriangles;
     }
-    return rc;
+    const int rcWait = lvn::meshgen_wait(ctx);
+    return rc < 0 ? rc : rcWait;
 }

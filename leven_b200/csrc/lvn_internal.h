@@ -187,4 +187,11 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
                     float4 *d_packP = nullptr, float physicsScale = 0.f);
 const char *simplify_last_error();
 
+// ---- api.cu: the fused chunk + simplifier batch, for clipmap_update.cu ----
+int generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize, const lvn_simplify_options *unitOptions,
+                        lvn_mesh_vertex *vertices, float *physicsVertices, float physicsScale, int64_t vertexCapacity,
+                        lvn_mesh_triangle *triangles, int64_t triangleCapacity, lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                        lvn_chunk_result *results, lvn_simplify_result *simplified, bool deferMeshCopies);
+int meshgen_wait(lvn_meshgen *ctx);
+
 }  // namespace lvn

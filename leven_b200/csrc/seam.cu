@@ -28,6 +28,7 @@
 // index triples with the same winding, in (owner vertex, edge) order instead of recursion order.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -170,7 +171,7 @@ __device__ long long g_seamTiming[16];      // [0..8) sums over blocks, [8..16) 
 
 __global__ void __launch_bounds__(SEAM_BLOCK)
 k_seam(const SeamJobDev *__restrict__ jobs, const int *__restrict__ launchOrder, const lvn_seam_neighbour *__restrict__ neighbours,
-       const lvn_seam_node_info *__restrict__ nodes, int voxelsPerChunk, SeamScratch ws,
+       const lvn_seam_node_info *__restrict__ nodes, int voxelsPerChunk, int forceGlobal, SeamScratch ws,
        lvn_mesh_vertex *__restrict__ vertices, int *__restrict__ triangles, int4 *__restrict__ results)
 {
     __shared__ int s_n, s_total, s_warp[SEAM_BLOCK / 32];
@@ -235,7 +236,7 @@ k_seam(const SeamJobDev *__restrict__ jobs, const int *__restrict__ launchOrder,
     // first of a run of equal keys is then the earliest selected, and a leaf's rank the number of run
     // heads before it.  Larger seams rank by counting through the global scratch.
     int n;
-    if (nSel <= SEAM_SMEM_KEYS) {
+    if (nSel <= SEAM_SMEM_KEYS && !forceGlobal) {
         int P = 32;
         while (P < nSel) P <<= 1;
         for (int i = tid; i < P; i += SEAM_BLOCK) s_keys[i] = i < nSel ? ((key[i] << 16) | (unsigned long long)i) : ~0ull;
@@ -302,7 +303,7 @@ k_seam(const SeamJobDev *__restrict__ jobs, const int *__restrict__ launchOrder,
 
     SPHASE(1);
     // ---- 3. leaves and all their ancestors into the table (Octree_ConstructUpwards) ----
-    const bool tableInSmem = (long long)n * (job.rootLog2 + 1) * 4 <= (long long)SEAM_SMEM_TABLE * 3;
+    const bool tableInSmem = !forceGlobal && (long long)n * (job.rootLog2 + 1) * 4 <= (long long)SEAM_SMEM_TABLE * 3;
     unsigned long long *tkeys = tableInSmem ? s_tkeys : ws.tableKeys + job.tableOffset;
     unsigned int *tvals = tableInSmem ? s_tvals : ws.tableVals + job.tableOffset;
     const unsigned int tmask = tableInSmem ? (unsigned int)(SEAM_SMEM_TABLE - 1) : job.tableMask;
@@ -327,7 +328,7 @@ k_seam(const SeamJobDev *__restrict__ jobs, const int *__restrict__ launchOrder,
     //      item by a select over the words.  Which survivors yield a quad is a second set of words. ----
     const int rootUnits = 1 << job.rootLog2;
     const int nItems = n * 12, nWords = (nItems + 31) >> 5;
-    const bool flagsInSmem = nWords <= SEAM_SMEM_WORDS;
+    const bool flagsInSmem = !forceGlobal && nWords <= SEAM_SMEM_WORDS;
     unsigned int *flagsA = flagsInSmem ? s_flags : reinterpret_cast<unsigned int *>(quadCount);
     int *prefA = flagsInSmem ? s_fpref : src;
     unsigned int *flagsB = flagsInSmem ? s_flagsB : reinterpret_cast<unsigned int *>(key);
@@ -564,7 +565,8 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
     static bool smemSet = false;
     if (!smemSet) { SCU(cudaFuncSetAttribute(k_seam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEAM_SMEM_BYTES)); smemSet = true; }
     k_seam<<<numSeams, SEAM_BLOCK, SEAM_SMEM_BYTES, st>>>((const SeamJobDev *)(B + oJobs), (const int *)(B + oOrder), (const lvn_seam_neighbour *)(B + oNb),
-                                            (const lvn_seam_node_info *)(B + oNodes), voxelsPerChunk, ws,
+                                            (const lvn_seam_node_info *)(B + oNodes), voxelsPerChunk,
+                                            getenv("LVN_SEAM_FORCE_GLOBAL") ? 1 : 0 /* test switch: the large-seam fallbacks on every seam */, ws,
                                             (lvn_mesh_vertex *)(B + oV), (int *)(B + oT), (int4 *)(B + oRes));
     SCU(cudaGetLastError());
 #ifdef LVN_SEAM_TIMING

@@ -26,6 +26,7 @@
 // _mm_rsqrt_ps := 1 / sqrt(x) (arithmetic spec; the x86 estimate differs between CPU vendors).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -829,6 +830,7 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     const int wordsE = ((maxEdges + 31) / 32 + 31) & ~31, wordsS = ((maxOther + 31) / 32 + 31) & ~31;
     int vtxSmem = (maxVerts + 31) & ~31;
     if (((size_t)wordsE + 2 * (size_t)wordsS + vtxSmem) * 8 > SIMP_MAX_SMEM) vtxSmem = 0;     // per-vertex arrays fall back to global memory
+    if (getenv("LVN_SIMP_FORCE_GLOBAL")) vtxSmem = 0;      // test switch: run the fallback on meshes that would fit
     const size_t smem = ((size_t)wordsE + 2 * (size_t)wordsS + vtxSmem) * 8;
     if (smem > 48 * 1024 && smem > g_simp.smemSet) {
         MCU(cudaFuncSetAttribute(k_simplify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIMP_MAX_SMEM));

@@ -315,3 +315,41 @@ def test_gpu_collision_batch(lc, world, surface_cy, golden, built):
         assert rc == 0 and P3.tobytes() == P.tobytes() and T3.tobytes() == T2.tobytes() and same(res3, res)
     finally:
         ctx.destroy()
+
+
+@pytest.mark.gpu
+def test_gpu_fallback_paths(lc, cases, golden, seams_of_world, surface_cy, monkeypatch):
+    """the scratch a block keeps in shared memory falls back to global slices for meshes / seams too
+    large for it; the switches force that path on inputs whose answers are known"""
+    import seam_scenarios as SS
+    from test_seam import seam_digest
+    rows, _ = golden
+    monkeypatch.setenv("LVN_SIMP_FORCE_GLOBAL", "1")
+    monkeypatch.setenv("LVN_SEAM_FORCE_GLOBAL", "1")
+    meshes = [(S.as_vertices(v), t, off) for name, v, t, off, opt in cases]
+    opts = [lc.SimplifyOptions.make(**opt) for name, v, t, off, opt in cases]
+    rc, out, res = lc.ngMeshSimplifierBatch(meshes, opts)
+    assert rc == 0
+    for (name, *_), (gv, gt) in zip(cases, out):
+        gvv = S.as_vertices(gv)
+        assert (str(len(gvv)), str(len(gt)), sha(gvv), sha(gt["indices_"])) == tuple(rows[name][4:]), name
+    want = np.load(os.path.join(ROOT, "tests", "golden", "ref_seams.npz"))["mixed_lod01"]
+    jobs = SS.build_jobs(SS.mixed_lod01(surface_cy), seams_of_world)
+    rc, sm, sres = lc.GenerateClipmapSeamMeshes(64, jobs)
+    assert rc == 0
+    for (gv, gt), w in zip(sm, want):
+        assert tuple(str(x) for x in seam_digest(gv, gt["indices_"])) == tuple(str(x) for x in w)
+
+
+@pytest.fixture(scope="module")
+def seams_of_world(world):
+    cache = {}
+
+    def get(mn, size):
+        k = (tuple(mn), size)
+        if k not in cache:
+            r = world.generate_chunk_mesh(list(mn), size)
+            world.free_chunk_octree(list(mn), size)
+            cache[k] = r["seams"]
+        return cache[k]
+    return get
