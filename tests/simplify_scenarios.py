@@ -148,6 +148,10 @@ def all_cases(world, oracle_mod, cy, csg_world=None):
     cases.append(("torus_two_materials", v, t, [0.0, 0.0, 0.0], dict(slack, edgeFraction=1.0, minAngleCosine=0.2, maxIterations=20)))
     v, t = fan()
     cases.append(("fan_high_degree", v, t, [0.0, 0.0, 0.0], dict(slack, edgeFraction=1.0)))
+    # MeshBuffer's capacity (render_types.h:63-68: 14 336 vertices, 28 672 triangles), every edge sampled: the
+    # largest mesh the reference can hold, the kernel's largest shared-memory footprint
+    v, t = grid_plane(119, 4.0, 0.8, seed=7)
+    cases.append(("plane_max_size", v, t, [236.0, 0.0, 236.0], dict(slack, edgeFraction=1.0, minAngleCosine=0.3)))
     v, t = grid_plane(7, 4.0, 0.0)          # 72 triangles: under the 100-triangle floor, returned untouched
     cases.append(("too_small", v, t, [12.0, 0.0, 12.0], slack))
     v, t = grid_plane(8, 4.0, 0.0)          # 98 triangles / 64 vertices
