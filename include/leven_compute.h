@@ -362,6 +362,20 @@ int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *nodes, int numA
                              int32_t *seamUpdateNodes, lvn_seam_result *seamResults, const float seamColour[3],
                              lvn_clipmap_update_totals *totals);
 
+/* Pass 2 of the update on its own, shardable: the seam-update set (clipmap.cpp:1306-1324) over the
+ * active nodes nodes[active[..]] around the newly active nodes nodes[constructed[..]], and
+ * GenerateClipmapSeamMesh for the share of the set this caller takes -- entry u of the ascending set
+ * belongs to shard u % shardCount (seams are independent of each other).  seamNodes may be host or
+ * device memory (e.g. the all-gathered seam nodes of every GPU's nodes).  *numSeamUpdatesAll = size
+ * of the whole set, *numSeamUpdatesMine = entries of seamUpdateNodes / seamResults filled. */
+int lvn_clipmap_seam_update_batch(int voxelsPerChunk, const lvn_clipmap_node *nodes, int numNodes,
+                                  const int32_t *active, int numActive, const int32_t *constructed, int numConstructed,
+                                  const lvn_seam_node_info *seamNodes, int64_t numSeamNodes, int shardIndex, int shardCount,
+                                  lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                  lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                  int32_t *seamUpdateNodes, lvn_seam_result *seamResults, const float seamColour[3],
+                                  int32_t *numSeamUpdatesAll, int32_t *numSeamUpdatesMine);
+
 /* ---- utilities of the path (a9, a15), usable on their own ---------------- */
 
 /* FindNextPrime, primes.h (primes.cpp:32-59) */

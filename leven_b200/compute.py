@@ -134,6 +134,7 @@ ABI = {
     "lvn_mesh_simplify_batch": (_I, [_I, _P, _P, _I, _P, _I64, _P, _I64, _P]),
     "lvn_mesh_simplify_last_error": (C.c_char_p, []),
     "lvn_meshgen_generate_simplified_batch": (_I, [_P, _I, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
+    "lvn_clipmap_seam_update_batch": (_I, [_I, _P, _I, _P, _I, _P, _I, _P, _I64, _I, _I, _P, _I64, _P, _I64, _P, _P, _P, _P, _P]),
     "lvn_clipmap_update_batch": (_I, [_P, _P, _I, _I, _P, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _P]),
     "lvn_meshgen_generate_collision_batch": (_I, [_P, _I, _P, _P, C.c_float, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
 }
@@ -680,3 +681,21 @@ def ClipmapUpdateBatch(ctx, nodes, numActive, seamNodes, seamNodesUsed, vertices
                                         _ptr(seamNodes), int(seamNodesUsed), len(seamNodes), _ptr(vertices), len(vertices),
                                         _ptr(triangles), len(triangles), _ptr(cres), _ptr(upd), _ptr(sres), col, C.byref(tot))
     return rc, cres[:n_construct], upd[:tot.numSeamUpdates], sres[:tot.numSeamUpdates], tot
+
+
+def ClipmapSeamUpdateBatch(voxelsPerChunk, nodes, active, constructed, seamNodes, numSeamNodes, vertices, triangles,
+                           shardIndex=0, shardCount=1, colour=(1.0, 1.0, 1.0)):
+    """lvn_clipmap_seam_update_batch: pass 2 of an update for one shard of the seam-update set.
+    seamNodes: a numpy SeamNodeInfo array, or an integer device address (the all-gathered arena).
+    -> (rc, seamUpdateNodes, seamResults, numSeamUpdatesAll)"""
+    active = np.ascontiguousarray(active, np.int32); constructed = np.ascontiguousarray(constructed, np.int32)
+    upd = np.zeros(max(len(nodes), 1), np.int32)
+    sres = np.zeros(max(len(nodes), 1), SeamResult)
+    n_all, n_mine = C.c_int32(0), C.c_int32(0)
+    col = (C.c_float * 3)(*colour)
+    sn = C.c_void_p(int(seamNodes)) if isinstance(seamNodes, int) else _ptr(seamNodes)
+    rc = lib().lvn_clipmap_seam_update_batch(int(voxelsPerChunk), _ptr(nodes), len(nodes), _ptr(active), len(active), _ptr(constructed),
+                                             len(constructed), sn, int(numSeamNodes), int(shardIndex), int(shardCount),
+                                             _ptr(vertices), len(vertices), _ptr(triangles), len(triangles), _ptr(upd), _ptr(sres), col,
+                                             C.byref(n_all), C.byref(n_mine))
+    return rc, upd[:n_mine.value], sres[:n_mine.value], n_all.value

@@ -71,6 +71,84 @@ struct ActiveIndex {
 
 }  // namespace
 
+// Pass 2 on its own: the seam-update set of an update (clipmap.cpp:1306-1324) over the nodes listed in
+// `active`, and GenerateClipmapSeamMesh (clipmap.cpp:573-611) for the share of that set this caller
+// takes: entry u of the (ascending) set belongs to shard u % shardCount.  With one GPU the share is
+// everything; with G GPUs every rank holds all nodes' seam nodes after the exchange (host or device
+// memory: the seam batch copies from either) and contours the seams of its share.
+extern "C" int lvn_clipmap_seam_update_batch(int voxelsPerChunk, const lvn_clipmap_node *nodes, int numNodes,
+                                             const int32_t *active, int numActive, const int32_t *constructed, int numConstructed,
+                                             const lvn_seam_node_info *seamNodes, int64_t numSeamNodes, int shardIndex, int shardCount,
+                                             lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                             lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                             int32_t *seamUpdateNodes, lvn_seam_result *seamResults, const float seamColour[3],
+                                             int32_t *numSeamUpdatesAll, int32_t *numSeamUpdatesMine)
+{
+    if (numNodes < 0 || numActive < 0 || numConstructed < 0 || shardCount < 1 || shardIndex < 0 || shardIndex >= shardCount ||
+        !numSeamUpdatesAll || !numSeamUpdatesMine || (numActive > 0 && (!nodes || !active)) || (numConstructed > 0 && !constructed))
+        return LVN_ERR_INVALID_VALUE;
+    *numSeamUpdatesAll = 0; *numSeamUpdatesMine = 0;
+    std::vector<int> act(active, active + numActive);
+    for (int a : act) if (a < 0 || a >= numNodes) return LVN_ERR_INVALID_VALUE;
+    for (int c = 0; c < numConstructed; c++) if (constructed[c] < 0 || constructed[c] >= numNodes) return LVN_ERR_INVALID_VALUE;
+    ActiveIndex index;
+    index.build(nodes, act);
+    std::vector<char> marked((size_t)numNodes, 0);
+    std::vector<int> found;
+    for (int k = 0; k < numConstructed; k++) {
+        const int c = constructed[k];
+        for (int i = 0; i < 8; i++) {
+            int cmin[3];
+            for (int a = 0; a < 3; a++) cmin[a] = nodes[c].min[a] - kChildMinOffsets[i][a] * nodes[c].size;
+            found.clear();
+            index.query(cmin, nodes[c].size, found);
+            for (int f : found) marked[f] = 1;
+        }
+    }
+    std::vector<int> updates;
+    int all = 0;
+    for (int i = 0; i < numNodes; i++)
+        if (marked[i]) { if (all % shardCount == shardIndex) updates.push_back(i); all++; }   // (the reference iterates an unordered_set)
+    *numSeamUpdatesAll = all;
+    *numSeamUpdatesMine = (int32_t)updates.size();
+    if (updates.empty()) return LVN_SUCCESS;
+    if (!seamUpdateNodes || !seamResults) return LVN_ERR_INVALID_VALUE;
+
+    std::vector<lvn_seam_job> jobs(updates.size());
+    std::vector<lvn_seam_neighbour> nbs;
+    for (size_t u = 0; u < updates.size(); u++) {
+        const lvn_clipmap_node &h = nodes[updates[u]];
+        seamUpdateNodes[u] = updates[u];
+        lvn_seam_job &j = jobs[u];
+        memset(&j, 0, sizeof(j));
+        memcpy(j.hostMin, h.min, sizeof(j.hostMin));
+        j.hostSize = h.size;
+        j.firstNeighbour = (int32_t)nbs.size();
+        for (int a = 0; a < 3; a++) j.colour[a] = seamColour ? seamColour[a] : 1.f;
+        for (int i = 0; i < 8; i++) {
+            int cmin[3];
+            for (int a = 0; a < 3; a++) cmin[a] = h.min[a] + kChildMinOffsets[i][a] * h.size;
+            found.clear();
+            index.query(cmin, h.size, found);
+            for (int f : found) {
+                const lvn_clipmap_node &nb = nodes[f];
+                if (nb.numSeamNodes <= 0) continue;
+                lvn_seam_neighbour sn;
+                memset(&sn, 0, sizeof(sn));
+                sn.index = i;
+                memcpy(sn.min, nb.min, sizeof(sn.min));
+                sn.size = nb.size;
+                sn.firstNode = nb.firstSeamNode;
+                sn.numNodes = nb.numSeamNodes;
+                nbs.push_back(sn);
+            }
+        }
+        j.numNeighbours = (int32_t)nbs.size() - j.firstNeighbour;
+    }
+    return lvn_seam_mesh_generate_batch(voxelsPerChunk, (int)jobs.size(), jobs.data(), nbs.data(), (int)nbs.size(), seamNodes, (int)numSeamNodes,
+                                        vertices, vertexCapacity, triangles, triangleCapacity, seamResults);
+}
+
 extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *nodes, int numActive, int numConstruct,
                                         const lvn_simplify_options *unitOptions,
                                         lvn_seam_node_info *seamNodes, int64_t seamNodesUsed, int64_t seamCapacity,
@@ -131,62 +209,14 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
         }
     totals->numConstructedActive = (int32_t)constructed.size();
 
-    // ---- 2. the seam-update set (clipmap.cpp:1306-1324) ----
-    ActiveIndex index;
-    index.build(nodes, active);
-    std::vector<char> marked((size_t)numActive + numConstruct, 0);
-    std::vector<int> found;
-    for (int c : constructed)
-        for (int i = 0; i < 8; i++) {
-            int cmin[3];
-            for (int a = 0; a < 3; a++) cmin[a] = nodes[c].min[a] - kChildMinOffsets[i][a] * nodes[c].size;
-            found.clear();
-            index.query(cmin, nodes[c].size, found);
-            for (int f : found) marked[f] = 1;
-        }
-    std::vector<int> updates;
-    for (int i = 0; i < numActive + numConstruct; i++) if (marked[i]) updates.push_back(i);   // (the reference iterates an unordered_set)
-    totals->numSeamUpdates = (int32_t)updates.size();
-    if (updates.empty()) return lvn::meshgen_wait(ctx);
-
-    // ---- 3. GenerateClipmapSeamMesh for the whole set (clipmap.cpp:573-611) ----
-    std::vector<lvn_seam_job> jobs(updates.size());
-    std::vector<lvn_seam_neighbour> nbs;
-    for (size_t u = 0; u < updates.size(); u++) {
-        const lvn_clipmap_node &h = nodes[updates[u]];
-        seamUpdateNodes[u] = updates[u];
-        lvn_seam_job &j = jobs[u];
-        memset(&j, 0, sizeof(j));
-        memcpy(j.hostMin, h.min, sizeof(j.hostMin));
-        j.hostSize = h.size;
-        j.firstNeighbour = (int32_t)nbs.size();
-        for (int a = 0; a < 3; a++) j.colour[a] = seamColour ? seamColour[a] : 1.f;
-        for (int i = 0; i < 8; i++) {
-            int cmin[3];
-            for (int a = 0; a < 3; a++) cmin[a] = h.min[a] + kChildMinOffsets[i][a] * h.size;
-            found.clear();
-            index.query(cmin, h.size, found);
-            for (int f : found) {
-                const lvn_clipmap_node &nb = nodes[f];
-                if (nb.numSeamNodes <= 0) continue;
-                lvn_seam_neighbour s;
-                memset(&s, 0, sizeof(s));
-                s.index = i;
-                memcpy(s.min, nb.min, sizeof(s.min));
-                s.size = nb.size;
-                s.firstNode = nb.firstSeamNode;
-                s.numNodes = nb.numSeamNodes;
-                nbs.push_back(s);
-            }
-        }
-        j.numNeighbours = (int32_t)nbs.size() - j.firstNeighbour;
-    }
-    // the seam meshes follow the node meshes in the two arenas
-    const int rc = lvn_seam_mesh_generate_batch(V, (int)jobs.size(), jobs.data(), nbs.data(), (int)nbs.size(), seamNodes, (int)totals->seamNodesUsed,
-                                                vertices ? vertices + totals->nodeVertices : nullptr, vertexCapacity - totals->nodeVertices,
-                                                triangles ? triangles + totals->nodeTriangles : nullptr, triangleCapacity - totals->nodeTriangles,
-                                                seamResults);
-    for (size_t u = 0; u < updates.size(); u++) {
+    // ---- 2 + 3. the seam-update set and its seam meshes, after the node meshes in the two arenas ----
+    int32_t numMine = 0;
+    const int rc = lvn_clipmap_seam_update_batch(V, nodes, numActive + numConstruct, active.data(), (int)active.size(),
+                                                 constructed.data(), (int)constructed.size(), seamNodes, totals->seamNodesUsed, 0, 1,
+                                                 vertices ? vertices + totals->nodeVertices : nullptr, vertexCapacity - totals->nodeVertices,
+                                                 triangles ? triangles + totals->nodeTriangles : nullptr, triangleCapacity - totals->nodeTriangles,
+                                                 seamUpdateNodes, seamResults, seamColour, &totals->numSeamUpdates, &numMine);
+    for (int u = 0; u < numMine; u++) {
         lvn_seam_result &r = seamResults[u];
         totals->seamVertices += r.numVertices; totals->seamTriangles += r.numTriangles;
         r.vertexOffset += (int32_t)totals->nodeVertices;

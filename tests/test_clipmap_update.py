@@ -128,3 +128,45 @@ def test_gpu_update_incremental(lc, surface_cy, built):
         assert rc == lc.LVN_ERR_CAPACITY
     finally:
         ctx.destroy()
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_update_pieces(lc, surface_cy, built):
+    """the pieces the multi-GPU update is made of (leven_b200/sharding.py), on one GPU: pass 2 taken
+    in two shares gives, together, exactly the seams of the one-call update; the single-process form
+    of sharded_clipmap_update equals lvn_clipmap_update_batch; the seam nodes may sit in device memory"""
+    import torch
+    from leven_b200 import sharding
+    cover = S.mixed_lod01(surface_cy)
+    ms = np.array([list(mn) + [size] for mn, size in cover], np.int32)
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        nodes = np.zeros(len(cover), lc.ClipmapNode)
+        nodes["min"] = ms[:, :3]; nodes["size"] = ms[:, 3]
+        V = np.zeros(400000, lc.MeshVertex); T = np.zeros(800000, lc.MeshTriangle); Sn = np.zeros(200000, lc.SeamNodeInfo)
+        cres, upd, sres, tot = run_update(lc, ctx, nodes, 0, Sn, 0, V, T)
+        whole = {int(k): seam_digest(V[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]],
+                                     T["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]]) for k, r in zip(upd, sres)}
+        active = np.array([k for k, r in enumerate(cres) if r["numTriangles"] > 0 or r["numSeamNodes"] > 0], np.int32)
+        dev = torch.from_numpy(Sn[:tot.seamNodesUsed].view(np.uint8).reshape(-1).copy()).cuda()      # shard 1 reads device memory
+        got = {}
+        for shard, arena in ((0, Sn), (1, int(dev.data_ptr()))):
+            V2 = np.zeros(100000, lc.MeshVertex); T2 = np.zeros(100000, lc.MeshTriangle)
+            rc, u2, s2, n_all = lc.ClipmapSeamUpdateBatch(64, nodes, active, active, arena, tot.seamNodesUsed, V2, T2, shard, 2)
+            assert rc == 0 and n_all == len(upd) and len(u2) in (len(upd) // 2, (len(upd) + 1) // 2)
+            assert u2.tolist() == upd[shard::2].tolist()
+            for k, r in zip(u2, s2):
+                got[int(k)] = seam_digest(V2[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]],
+                                          T2["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]])
+        assert got == whole and len(got) > 10
+        # world size 1: the same answer through the sharded driver
+        V3 = np.zeros(400000, lc.MeshVertex); T3 = np.zeros(800000, lc.MeshTriangle); S3 = np.zeros(200000, lc.SeamNodeInfo)
+        out = sharding.sharded_clipmap_update(lc, ctx, ms, V3, T3, S3)
+        assert out["seam_update_nodes"].tolist() == upd.tolist() and out["num_seam_updates_all"] == len(upd)
+        assert out["node_totals"] == (tot.nodeVertices, tot.nodeTriangles)
+        assert V3[:tot.nodeVertices].tobytes() == V[:tot.nodeVertices].tobytes()
+        for k, r in zip(out["seam_update_nodes"], out["seam_results"]):
+            assert seam_digest(V3[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]],
+                               T3["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]]) == whole[int(k)]
+    finally:
+        ctx.destroy()

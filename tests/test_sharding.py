@@ -69,3 +69,51 @@ def test_world_size_2_gloo_count_gather(tmp_path, built, surface_cy):
     assert np.array_equal(r0["counts"], ref)
     assert np.array_equal(r0["offsets"], np.cumsum(ref, axis=0) - ref)
     assert np.array_equal(r0["totals"], ref.sum(axis=0)) and ref.sum() > 0
+
+
+def _exchange_worker(rank, world_size, port, nodes, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from leven_b200 import sharding
+    from oracle import oracle as O
+    mine = sharding.shard_round_robin(len(nodes), rank, world_size)
+    world = O.World(seed=SEED)
+    tris, counts, offsets, parts, used = [], [], [], [], 0
+    for i in mine:          # this rank's pass 1 (the oracle stands in for the CUDA path in this suite)
+        r = world.generate_chunk_mesh(list(nodes[i][:3]), int(nodes[i][3]))
+        world.free_chunk_octree(list(nodes[i][:3]), int(nodes[i][3]))
+        tris.append(r["numTriangles"]); counts.append(len(r["seams"])); offsets.append(used)
+        parts.append(r["seams"]); used += len(r["seams"])
+    local = np.concatenate(parts) if used else np.zeros(0, parts[0].dtype if parts else np.uint8)
+    table, arena, per_rank = sharding.exchange_seam_nodes(len(nodes), mine, tris, counts, offsets, local)
+    np.savez(os.path.join(out_dir, f"x{rank}.npz"), table=table, arena=np.asarray(arena), per_rank=per_rank, mine=mine)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_seam_node_exchange(tmp_path, built, surface_cy):
+    """the one exchange step of the batched update over G GPUs (leven_b200/sharding.py): after it every
+    rank holds every node's triangle count and seam nodes, addressed through the same table"""
+    from oracle import oracle as O
+    nodes = np.array([[cx * 256, (surface_cy + dy) * 256, cz * 256, 256] for dy in (-1, 0) for cx in (-1, 0) for cz in (-1, 0, 1)]
+                     + [[0, 15 * 256, 0, 256]], np.int32)          # 12 surface-side nodes + one of air
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(2, port, nodes, str(tmp_path)), nprocs=2, join=True)
+    x0, x1 = np.load(tmp_path / "x0.npz"), np.load(tmp_path / "x1.npz")
+    assert np.array_equal(x0["table"], x1["table"]) and x0["arena"].tobytes() == x1["arena"].tobytes()
+    assert x0["per_rank"] == x1["per_rank"] and len(x0["arena"]) == 2 * int(x0["per_rank"]) * 48
+    world = O.World(seed=SEED)
+    seen = 0
+    for i, n in enumerate(nodes):
+        r = world.generate_chunk_mesh(list(n[:3]), int(n[3]))
+        world.free_chunk_octree(list(n[:3]), int(n[3]))
+        tri, cnt, first = (int(v) for v in x0["table"][i])
+        assert tri == r["numTriangles"] and cnt == len(r["seams"])
+        got = x0["arena"][first * 48:(first + cnt) * 48]
+        assert got.tobytes() == np.ascontiguousarray(r["seams"]).tobytes(), i
+        seen += cnt
+    assert seen > 1000 and x0["table"][-1].tolist() == [0, 0, 0]
