@@ -243,6 +243,11 @@ def main():
         return float(t.item())
 
     assert lc.Compute_SetDevice(local_rank) == 0
+    # one process per GPU: keep this process and the pinned arenas it allocates below on the GPU's
+    # socket (LVN_NUMA_BIND=0 leaves the scheduler's placement alone)
+    numa = (-1, 0, False)
+    if os.environ.get("LVN_NUMA_BIND", "1") != "0":
+        numa = lc.Compute_BindHostNuma(local_rank)
     rc = lc.Compute_Initialise(SEED, 0, 2)
     assert rc == 0, f"Compute_Initialise: {lc.GetCLErrorString(rc)} {lc.last_cuda_error()}"
     ctx = lc.Compute_MeshGenContext.create(V)
@@ -423,6 +428,8 @@ def main():
         "stages": stages,
         "serial_ms_per_step": prof_ms / prof_steps,
         "pipeline": {"device": {"lanes": pipe[0], "streams": pipe[1]}, "e2e": {"lanes": pipe_e2e[0], "streams": pipe_e2e[1]}},
+        "host_numa": {"node": numa[0], "cpus_bound": numa[1], "memory_policy_set": numa[2],
+                      "what": "rank 0's binding to its GPU's NUMA node before the pinned arenas are allocated (lvn_compute_bind_host_numa; node < 0: the platform names none)"},
     }
 
     if world_size == 1 and not args.no_cpu_baseline:

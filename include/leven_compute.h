@@ -74,6 +74,11 @@ typedef struct lvn_aabb { int32_t min[3], max[3]; } lvn_aabb;
 
 /* new: choose the CUDA device before lvn_compute_initialise (one process per GPU) */
 int lvn_compute_set_device(int cudaDevice);
+/* new: keep the calling thread and the pinned memory it allocates afterwards on the NUMA node the
+ * device is attached to (one process per GPU on a multi-socket host).  Returns the node, negative
+ * when the platform names none (nothing changed); *cpusBound = CPUs in the new affinity mask (0 =
+ * left alone), *memoryBound = 1 when the preferred-node policy was set.  Optional, off by default. */
+int lvn_compute_bind_host_numa(int cudaDevice, int *cpusBound, int *memoryBound);
 
 /* Compute_Initialise, compute.h:35 (compute.cpp:195-234) */
 int lvn_compute_initialise(int noiseSeed, unsigned int defaultMaterial, int numCSGBrushes);

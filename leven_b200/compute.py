@@ -90,6 +90,7 @@ class StageStats(C.Structure):
 _P, _I, _U, _F, _I64 = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_int64
 ABI = {
     "lvn_compute_set_device": (_I, [_I]),
+    "lvn_compute_bind_host_numa": (_I, [_I, _P, _P]),
     "lvn_compute_initialise": (_I, [_I, _U, _I]),
     "lvn_compute_shutdown": (_I, []),
     "lvn_compute_set_noise_seed": (_I, [_I]),
@@ -178,6 +179,13 @@ def last_cuda_error():
 
 def Compute_SetDevice(device):
     return lib().lvn_compute_set_device(int(device))
+
+
+def Compute_BindHostNuma(device):
+    """lvn_compute_bind_host_numa -> (node or negative, cpus in the new affinity mask, memory policy set)"""
+    cpus, mem = C.c_int(0), C.c_int(0)
+    node = lib().lvn_compute_bind_host_numa(int(device), C.byref(cpus), C.byref(mem))
+    return node, cpus.value, bool(mem.value)
 
 
 def Compute_Initialise(noiseSeed, defaultMaterial, numCSGBrushes):

@@ -14,6 +14,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <map>
@@ -145,6 +148,53 @@ extern "C" int lvn_compute_set_device(int cudaDevice)
     g.deviceChosen = true;
     CU(cudaSetDevice(cudaDevice));
     return LVN_SUCCESS;
+}
+
+// One process per GPU on a two-socket box: the pinned arenas a process allocates afterwards should
+// sit on the socket its GPU hangs off, or every download crosses the socket link and the ranks
+// share one memory controller.  Reads the device's PCI address, its NUMA node from sysfs, restricts
+// the calling thread (threads made later inherit it) to that node's CPUs -- those the process is
+// allowed to use -- and prefers the node for its page allocations.  Returns the node, or a negative
+// value when the platform gives no answer (nothing is changed then); cpusBound = CPUs in the new
+// mask (0: affinity left alone), memoryBound = 1 when set_mempolicy took.
+extern "C" int lvn_compute_bind_host_numa(int cudaDevice, int *cpusBound, int *memoryBound)
+{
+    if (cpusBound) *cpusBound = 0;
+    if (memoryBound) *memoryBound = 0;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), cudaDevice) != cudaSuccess) { cudaGetLastError(); return LVN_ERR_INVALID_VALUE; }
+    for (char *c = bus; *c; c++) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0 || node >= 1024) return -1;
+    // the node's CPUs, "a-b,c,d-e"
+    cpu_set_t want, have, both;
+    CPU_ZERO(&want);
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    if (FILE *f = fopen(path, "r")) {
+        int a, b;
+        while (fscanf(f, "%d", &a) == 1) {
+            b = a;
+            int ch = fgetc(f);
+            if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+            for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &want);
+            if (ch != ',') break;
+        }
+        fclose(f);
+    }
+    if (sched_getaffinity(0, sizeof(have), &have) == 0) {
+        CPU_AND(&both, &want, &have);
+        const int nb = CPU_COUNT(&both);
+        if (nb > 0 && sched_setaffinity(0, sizeof(both), &both) == 0 && cpusBound) *cpusBound = nb;
+    }
+    unsigned long mask[1024 / (8 * sizeof(unsigned long))] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+#ifdef SYS_set_mempolicy
+    if (syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024ul + 1) == 0 && memoryBound) *memoryBound = 1;
+#endif
+    return node;
 }
 
 // ---- noise table (compute_density_field.cpp:28-125) -------------------------
