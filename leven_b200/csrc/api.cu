@@ -445,7 +445,6 @@ struct lvn_meshgen {
     // batch workspace
     DevBuf<ChunkDesc> d_descs;
     DevBuf<ChunkHdr> d_hdrs;
-    DevBuf<int4> d_colOrigins;
     DevBuf<float> d_heights;
     DevBuf<unsigned long long> d_bitsLo;
     DevBuf<unsigned int> d_bitsHi, d_rowE, d_rowN, d_rowQ, d_rowS;
@@ -457,7 +456,6 @@ struct lvn_meshgen {
     DevBuf<lvn_seam_node_info> d_seams;
     DevBuf<uint4> d_slab;
     DevBuf<unsigned int> d_slabEy, d_ticket;
-    DevBuf<int> d_colMin, d_colMax;            // per column set: ordered-int keys of the height range
     DevBuf<TileRef> d_edgeTiles, d_nodeTiles;  // tile directories, one slice per lane
     DevBuf<uint8_t> d_tmpFields;
     DevBuf<uint8_t *> d_fieldPtrs;
@@ -564,13 +562,13 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     for (auto &kv : ctx->fields) kv.second.release(ctx->stream);
     for (auto &kv : ctx->octrees) kv.second.release(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_colOrigins.release(); ctx->d_heights.release();
+    ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_heights.release();
     ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
     ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release(); ctx->d_xzList.release();
     ctx->d_vertices.release(); ctx->d_tris.release(); ctx->d_seams.release();
     ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release();
     ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
-    ctx->d_colMin.release(); ctx->d_colMax.release(); ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
+    ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
     ctx->d_ops.release(); ctx->d_csgChunks.release();
@@ -818,7 +816,11 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     }
 
     // ---- descriptors (internal, lane-major order), column-set dedupe, cached fields ----
-    LV(ctx->h_descs.reserve(n));
+    // the batch head = the chunk descriptors, then (16-byte aligned) the column sets' origins and the
+    // initial keys of their height ranges: one pinned staging block, one upload
+    const size_t headColOffset = ((size_t)n * sizeof(ChunkDesc) + 15) & ~(size_t)15;
+    const size_t headDescs = (headColOffset + (size_t)n * (sizeof(int4) + 2 * sizeof(int)) + sizeof(ChunkDesc) - 1) / sizeof(ChunkDesc);
+    LV(ctx->h_descs.reserve(headDescs));
     LV(ctx->h_colOrigins.reserve(n));
     LV(ctx->h_hdrs.reserve(n + S));
     std::map<std::tuple<int, int, int>, int> colSets;
@@ -859,12 +861,9 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     }
 
     // ---- workspace ----
-    LV(ctx->d_descs.reserve(n));
+    LV(ctx->d_descs.reserve(headDescs));
     LV(ctx->d_hdrs.reserve(n + S));
-    LV(ctx->d_colOrigins.reserve(std::max(numColSets, 1)));
     LV(ctx->d_heights.reserve(std::max<size_t>((size_t)numColSets * FF, 1)));
-    LV(ctx->d_colMin.reserve(std::max(numColSets, 1)));
-    LV(ctx->d_colMax.reserve(std::max(numColSets, 1)));
     LV(ctx->d_bitsLo.reserve(n * FF));
     LV(ctx->d_bitsHi.reserve(n * FF));
     LV(ctx->d_rowE.reserve(n * HH));
@@ -890,9 +889,19 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     LV(ctx->d_tris.reserve(ctx->d_vertices.cap * 6 * 2));
     LV(ctx->d_seams.reserve(std::max<size_t>((size_t)n * 512, 1u << 14)));
 
-    CU(cudaMemcpyAsync(ctx->d_descs.p, ctx->h_descs.p, n * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
-    if (numColSets)
-        CU(cudaMemcpyAsync(ctx->d_colOrigins.p, ctx->h_colOrigins.p, numColSets * sizeof(int4), cudaMemcpyHostToDevice, st));
+    {
+        char *hb = (char *)ctx->h_descs.p + headColOffset;
+        memcpy(hb, ctx->h_colOrigins.p, (size_t)numColSets * sizeof(int4));
+        int *hMin = (int *)(hb + (size_t)numColSets * sizeof(int4)), *hMax = hMin + numColSets;
+        for (int k = 0; k < numColSets; k++) { hMin[k] = 0x7f7f7f7f; hMax[k] = (int)0x80808080u; }   // ordered keys of +3.4e38 / -3.4e38
+    }
+    {   // one upload instead of two and two memsets (measured against a kernel that reads the mapped staging
+        // block itself, profiles/r01s_notes.md: the copy is as fast or faster)
+        const size_t headBytes = headColOffset + (size_t)numColSets * (sizeof(int4) + 2 * sizeof(int));
+        CU(cudaMemcpyAsync(ctx->d_descs.p, ctx->h_descs.p, headBytes, cudaMemcpyHostToDevice, st));
+    }
+    const int4 *d_colOrigins = (const int4 *)((char *)ctx->d_descs.p + headColOffset);
+    int *d_colMin = (int *)(d_colOrigins + numColSets), *d_colMax = d_colMin + numColSets;
 
     const DensityParams dp = density_params();
     ChunkScratch ws;
@@ -902,10 +911,8 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
 
     // ---- S1 for the whole batch: the column sets are shared between the lanes ----
     if (numColSets) {
-        CU(cudaMemsetAsync(ctx->d_colMin.p, 0x7f, numColSets * sizeof(int), st));   // ordered key of +3.4e38
-        CU(cudaMemsetAsync(ctx->d_colMax.p, 0x80, numColSets * sizeof(int), st));   // ordered key of -3.4e38
         StageTimer t(ctx, LVN_STAGE_COLUMNS, 1);
-        launch_columns(dp, d, ctx->d_colOrigins.p, numColSets, ctx->d_heights.p, ctx->d_colMin.p, ctx->d_colMax.p, st);
+        launch_columns(dp, d, d_colOrigins, numColSets, ctx->d_heights.p, d_colMin, d_colMax, st);
         ctx->stats.terrainEvals += (int64_t)numColSets * (int64_t)FF;
     }
     if (numTmpFields) {
@@ -976,7 +983,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             ctx->laneBase[k] = lane.base;
             {
                 StageTimer t(ctx, LVN_STAGE_CLASSIFY, 1);
-                launch_rows(d, ctx->d_descs.p, first, cnt, ctx->d_heights.p, ctx->d_colMin.p, ctx->d_colMax.p, hdrs, nullptr,
+                launch_rows(d, ctx->d_descs.p, first, cnt, ctx->d_heights.p, d_colMin, d_colMax, hdrs, nullptr,
                             ws, lane, ls);
             }
             // The lane's headers and counters are final once k_rows has run.  On the host path they

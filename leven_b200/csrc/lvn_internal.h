@@ -111,7 +111,7 @@ struct NodeDebug {
 
 // ---- launchers (kernels_chunk.cu) ----------------------------------------
 // colMin / colMax: per column set, the ordered-int keys of the smallest / largest height
-// (initialise with memset 0x7f / 0x80 before launch_columns)
+// (initialised to 0x7f7f7f7f / 0x80808080 before launch_columns: they arrive with the batch head)
 void launch_columns(const DensityParams &dp, const Dims &d, const int4 *colSetOrigins, int numColSets,
                     float *heights, int *colMin, int *colMax, cudaStream_t s);
 void launch_field_from_heights(const Dims &d, const ChunkDesc *descs, int n, const float *heights,
