@@ -110,6 +110,22 @@ def test_no_device_fails_loudly(built):
     rc, out, res = lc.ngMeshSimplifierBatch([(v, t, [0, 0, 0])], lc.SimplifyOptions.make())
     assert rc == lc.LVN_ERR_NO_DEVICE and len(out[0][1]) == 0
     assert lc.GenerateClipmapSeamMeshes(64, [([0, 0, 0], 256, [])])[0] == lc.LVN_ERR_NO_DEVICE
+    # pass 2 of the update: the seam-update set is host logic (it is counted before the device is
+    # asked for anything): a 2 x 2 x 2 block of newly active nodes invalidates all eight seams, a
+    # ninth node two cells away none; the contouring itself then has no device to run on
+    nodes = np.zeros(9, lc.ClipmapNode)
+    nodes["min"][:8] = [[x * 256, y * 256, z * 256] for x in (0, 1) for y in (0, 1) for z in (0, 1)]
+    nodes["min"][8] = [1024, 1024, 1024]
+    nodes["size"] = 256
+    nodes["numSeamNodes"] = 1
+    everyone = np.arange(9, dtype=np.int32)
+    V = np.zeros(16, lc.MeshVertex); T = np.zeros(16, lc.MeshTriangle); arena = np.zeros(16, lc.SeamNodeInfo)
+    rc, upd, sres, n_all = lc.ClipmapSeamUpdateBatch(64, nodes, everyone, everyone[:8], arena, 16, V, T, 1, 2)
+    assert rc == lc.LVN_ERR_NO_DEVICE and n_all == 8 and upd.tolist() == [1, 3, 5, 7]
+    rc, upd, sres, n_all = lc.ClipmapSeamUpdateBatch(64, nodes, everyone, everyone[8:], arena, 16, V, T)
+    assert n_all == 1 and upd.tolist() == [8]
+    assert lc.ClipmapSeamUpdateBatch(64, nodes, everyone, everyone[:0], arena, 16, V, T)[::3] == (0, 0)
+    assert lc.ClipmapSeamUpdateBatch(64, nodes, everyone, everyone, arena, 16, V, T, 2, 2)[0] == lc.LVN_ERR_INVALID_VALUE
 
 
 def test_packed_fp32_is_not_contracted(built):
