@@ -19,6 +19,15 @@ for k, (mn, size) in enumerate(cover):
 V = np.zeros(200000, lc.MeshVertex); T = np.zeros(400000, lc.MeshTriangle); Sn = np.zeros(100000, lc.SeamNodeInfo)
 rc, cres, upd, sres, tot = lc.ClipmapUpdateBatch(ctx, nodes, 0, Sn, 0, V, T)
 assert rc == 0 and tot.numSeamUpdates > 0 and tot.nodeTriangles > 0
+# pass 2 on its own, in two shares, the second reading the seam nodes from device memory (the form
+# the multi-GPU update uses after the all-gather)
+import torch
+active = np.array([k for k, r in enumerate(cres) if r["numTriangles"] > 0 or r["numSeamNodes"] > 0], np.int32)
+dev = torch.from_numpy(Sn[:tot.seamNodesUsed].view(np.uint8).reshape(-1).copy()).cuda()
+for shard, arena in ((0, Sn), (1, int(dev.data_ptr()))):
+    V2 = np.zeros(100000, lc.MeshVertex); T2s = np.zeros(100000, lc.MeshTriangle)
+    rc, u2, s2, n_all = lc.ClipmapSeamUpdateBatch(64, nodes, active, active, arena, tot.seamNodesUsed, V2, T2s, shard, 2)
+    assert rc == 0 and n_all == tot.numSeamUpdates and len(u2) > 0
 y1 = (B.CY0 * 256 // 512) * 512
 P = np.zeros((100000, 4), np.float32); T2 = np.zeros((200000, 3), np.int32)
 rc, res, simp = ctx.generateCollisionBatch([[0, y1, 0, 512], [-512, y1, 0, 512]], P, T2, Sn)
