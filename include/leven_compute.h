@@ -301,8 +301,10 @@ const char *lvn_mesh_simplify_last_error(void);
  * options scaled by the node's leaf size (leafSize = LEAF_SIZE_SCALE * (size / CLIPMAP_LEAF_SIZE);
  * maxError = unitOptions->maxError * leafSize, maxEdgeSize likewise; unitOptions carries
  * Options::meshMaxError_ / meshMaxEdgeLen_ / meshMinCosAngle_, options.h:14-16).  The meshes never
- * leave HBM between the two steps; the host arenas receive the SIMPLIFIED meshes, densely packed in
- * chunk order, and the (unsimplified octree's) seam nodes.  results[i] addresses chunk i's slices
+ * leave HBM between the two steps; the host arenas receive the SIMPLIFIED meshes, densely packed
+ * (in chunk order, except that in a large batch the few largest meshes -- the ones the simplifier
+ * works on longest -- come last, so that the others can cross PCIe meanwhile), and the
+ * (unsimplified octree's) seam nodes.  results[i] addresses chunk i's slices
  * and holds the simplified counts (numEdges stays the chunk's Hermite edge count); simplified[i]
  * (may be NULL) adds the simplifier's iteration count (-2: the mesh was too large to simplify and
  * is returned as generated).  On LVN_ERR_CAPACITY the counts say what the caller must provide. */

@@ -471,6 +471,8 @@ struct lvn_meshgen {
     // simplified batch (lvn_meshgen_generate_simplified_batch)
     DevBuf<int4> d_simpRes;
     DevBuf<int2> d_packOff;
+    cudaStream_t simpStreamB = nullptr;    // the early group of a split simplifier launch (simplify.cu)
+    cudaEvent_t evSimpFork = nullptr, evSimpEarly = nullptr, evSimpJoin = nullptr;
     DevBuf<lvn_mesh_vertex> d_packV;
     DevBuf<float4> d_packP;
     DevBuf<int> d_packT;
@@ -574,6 +576,10 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_ops.release(); ctx->d_csgChunks.release();
     ctx->d_simpRes.release(); ctx->d_packOff.release(); ctx->d_packV.release(); ctx->d_packP.release(); ctx->d_packT.release();
     ctx->h_simpRes.release(); ctx->h_packOff.release();
+    if (ctx->simpStreamB) cudaStreamDestroy(ctx->simpStreamB);
+    if (ctx->evSimpFork) cudaEventDestroy(ctx->evSimpFork);
+    if (ctx->evSimpEarly) cudaEventDestroy(ctx->evSimpEarly);
+    if (ctx->evSimpJoin) cudaEventDestroy(ctx->evSimpJoin);
     ctx->h_descs.release(); ctx->h_hdrs.release(); ctx->h_colOrigins.release();
     ctx->h_small.release();
     for (int i = 0; i < 2 * LVN_NUM_STAGES; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1235,31 +1241,58 @@ int lvn::generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunk
     }
     const int M = (int)meshes.size();
     const int64_t totalSeams = ctx->lastCounters.seams;
-    int2 totals = make_int2(0, 0);
+    int2 totals = make_int2(0, 0), early = make_int2(0, 0);
+    SimplifySplit split = {};
     if (M > 0) {
+        if (!ctx->simpStreamB) {
+            CU(cudaStreamCreateWithFlags(&ctx->simpStreamB, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ctx->evSimpFork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->evSimpEarly, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->evSimpJoin, cudaEventDisableTiming));
+        }
         LV(ctx->d_simpRes.reserve(M));
-        LV(ctx->d_packOff.reserve((size_t)M + 1));
+        LV(ctx->d_packOff.reserve((size_t)M + 2));      // per mesh, [M] the totals, [M + 1] the end of the early region
         if (vertices) LV(ctx->d_packV.reserve(ctx->lastCounters.nodes));
         if (physicsVertices) LV(ctx->d_packP.reserve(ctx->lastCounters.nodes));
         LV(ctx->d_packT.reserve(6 * (size_t)ctx->lastCounters.quads));
         LV(ctx->h_simpRes.reserve(M));
-        LV(ctx->h_packOff.reserve((size_t)M + 1));
+        LV(ctx->h_packOff.reserve((size_t)M + 2));
+        split.streamB = ctx->simpStreamB; split.evFork = ctx->evSimpFork; split.evEarly = ctx->evSimpEarly;
+        split.d_earlyTotals = ctx->d_packOff.p + M + 1;
         const int rc = simplify_device(M, meshes.data(), ctx->d_vertices.p, ctx->d_tris.p, ctx->d_simpRes.p,
                                        vertices ? ctx->d_packV.p : nullptr, ctx->d_packT.p, ctx->d_packOff.p, ctx->d_packOff.p + M, st,
-                                       physicsVertices ? ctx->d_packP.p : nullptr, physicsScale);
+                                       physicsVertices ? ctx->d_packP.p : nullptr, physicsScale,
+                                       deferMeshCopies ? nullptr : &split);   // (a caller that defers overlaps the download itself)
         if (rc < 0) { g_lastCudaError = simplify_last_error(); return rc; }
         CU(cudaMemcpyAsync(ctx->h_simpRes.p, ctx->d_simpRes.p, sizeof(int4) * M, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ctx->h_packOff.p, ctx->d_packOff.p, sizeof(int2) * ((size_t)M + 1), cudaMemcpyDeviceToHost, st));
     }
-    // the seam nodes do not wait for the simplifier: lane by lane (each lane's slice is dense)
+    // The seam nodes do not wait for the simplifier: lane by lane (each lane's slice is dense).  With a
+    // split launch they ride on the early group's stream, which ends long before the late group.
+    const bool splitRun = split.numEarly > 0;
+    cudaStream_t sideStream = splitRun ? ctx->simpStreamB : st;
+    if (splitRun) CU(cudaMemcpyAsync(ctx->h_packOff.p + M + 1, ctx->d_packOff.p + M + 1, sizeof(int2), cudaMemcpyDeviceToHost, sideStream));
     const bool seamsFit = totalSeams <= seamCapacity && (seamNodes || totalSeams == 0);
     int64_t hs = 0;
     for (int k = 0; k < ctx->numLanes; k++) {
         const unsigned int cnt = ctx->laneCounters[k].seams;
         ctx->hostBase[k][2] = hs;
         if (seamsFit && cnt)
-            CU(cudaMemcpyAsync(seamNodes + hs, ctx->d_seams.p + ctx->laneBase[k].seams, sizeof(lvn_seam_node_info) * cnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(seamNodes + hs, ctx->d_seams.p + ctx->laneBase[k].seams, sizeof(lvn_seam_node_info) * cnt, cudaMemcpyDeviceToHost, sideStream));
         hs += cnt;
+    }
+    if (splitRun) {
+        // the early region goes out while the largest meshes are still being simplified
+        CU(cudaStreamSynchronize(sideStream));
+        early = ctx->h_packOff.p[M + 1];
+        const bool fits = early.x <= vertexCapacity && early.y <= triangleCapacity && (early.x == 0 || vertices || physicsVertices) &&
+                          (early.y == 0 || triangles);
+        if (!fits) early = make_int2(0, 0);      // everything is decided (and refused) below, once the totals are known
+        if (early.x && vertices) CU(cudaMemcpyAsync(vertices, ctx->d_packV.p, sizeof(lvn_mesh_vertex) * (size_t)early.x, cudaMemcpyDeviceToHost, sideStream));
+        if (early.x && physicsVertices) CU(cudaMemcpyAsync(physicsVertices, ctx->d_packP.p, sizeof(float4) * (size_t)early.x, cudaMemcpyDeviceToHost, sideStream));
+        if (early.y) CU(cudaMemcpyAsync(triangles, ctx->d_packT.p, 12 * (size_t)early.y, cudaMemcpyDeviceToHost, sideStream));
+        CU(cudaEventRecord(ctx->evSimpJoin, sideStream));
+        CU(cudaStreamWaitEvent(st, ctx->evSimpJoin, 0));     // whoever waits for the context's stream waits for these copies too
     }
     CU(cudaStreamSynchronize(st));
     if (M > 0) totals = ctx->h_packOff.p[M];
@@ -1279,9 +1312,11 @@ int lvn::generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunk
     // on LVN_ERR_CAPACITY the counts say what the caller must provide
     if (!seamsFit || totals.x > vertexCapacity || totals.y > triangleCapacity ||
         (totals.x > 0 && !vertices && !physicsVertices) || (totals.y > 0 && !triangles)) return LVN_ERR_CAPACITY;
-    if (totals.x && vertices) CU(cudaMemcpyAsync(vertices, ctx->d_packV.p, sizeof(lvn_mesh_vertex) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
-    if (totals.x && physicsVertices) CU(cudaMemcpyAsync(physicsVertices, ctx->d_packP.p, sizeof(float4) * (size_t)totals.x, cudaMemcpyDeviceToHost, st));
-    if (totals.y) CU(cudaMemcpyAsync(triangles, ctx->d_packT.p, 12 * (size_t)totals.y, cudaMemcpyDeviceToHost, st));
+    // what has not left yet: everything, or the late group's region behind the early one
+    const size_t v0 = (size_t)early.x, t0 = (size_t)early.y, nv = (size_t)totals.x - v0, nt = (size_t)totals.y - t0;
+    if (nv && vertices) CU(cudaMemcpyAsync(vertices + v0, ctx->d_packV.p + v0, sizeof(lvn_mesh_vertex) * nv, cudaMemcpyDeviceToHost, st));
+    if (nv && physicsVertices) CU(cudaMemcpyAsync(physicsVertices + 4 * v0, ctx->d_packP.p + v0, sizeof(float4) * nv, cudaMemcpyDeviceToHost, st));
+    if (nt) CU(cudaMemcpyAsync(triangles + t0, ctx->d_packT.p + 3 * t0, 12 * nt, cudaMemcpyDeviceToHost, st));
     if (!deferMeshCopies) CU(cudaStreamSynchronize(st));
     return LVN_SUCCESS;
 }

@@ -182,9 +182,17 @@ struct SimplifyMesh {
 // iterations -1: a wild triangle index, -2: too large; both leave the mesh untouched.
 // With d_packT the simplified meshes are also gathered densely in mesh order (d_packV: MeshVertex,
 // d_packP: the physics engine's vec4 = (xyz - offset) * physicsScale; either may be null).
+// split (optional, packing only): the smaller meshes run and are packed on a second stream, at the
+// front of the packed arrays, while the largest ones are still being simplified (simplify.cu).
+struct SimplifySplit {
+    cudaStream_t streamB;        // in: the second stream
+    cudaEvent_t evFork, evEarly; // in: two events to order the streams with
+    int2 *d_earlyTotals;         // in: device word that receives the end of the early region
+    int numEarly;                // out: meshes in the early group; 0 = one launch, mesh order
+};
 int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int *d_T, int4 *d_results,
                     lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st,
-                    float4 *d_packP = nullptr, float physicsScale = 0.f);
+                    float4 *d_packP = nullptr, float physicsScale = 0.f, SimplifySplit *split = nullptr);
 const char *simplify_last_error();
 
 // ---- api.cu: the fused chunk + simplifier batch, for clipmap_update.cu ----

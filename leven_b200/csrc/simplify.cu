@@ -706,27 +706,29 @@ k_simplify(const SimpJobDev *__restrict__ jobs, SimpScratch ws, lvn_mesh_vertex 
     if (tid == 0) results[job.result] = make_int4(newNV, NT, iterations, NE);
 }
 
-// The simplified meshes, left at the start of their slices, gathered into dense arrays in mesh
-// order: one block per mesh; a mesh's place = the counts of the meshes before it.
+// The simplified meshes, left at the start of their slices, gathered into dense arrays in the order
+// of the list: one block per listed mesh; a mesh's place = *baseFrom (the end of an earlier group's
+// region; null = 0) + the counts of the listed meshes before it.  results / packedOffsets are
+// indexed by the mesh's own number (job.result); *totals = where this group's region ends.
 __global__ void __launch_bounds__(256)
 k_pack_meshes(const SimpJobDev *__restrict__ jobsByMesh, const int4 *__restrict__ results, int numMeshes,
               const lvn_mesh_vertex *__restrict__ V, const int *__restrict__ T,
               lvn_mesh_vertex *__restrict__ outV, int *__restrict__ outT, int2 *__restrict__ packedOffsets, int2 *__restrict__ totals,
-              float4 *__restrict__ outP, float physicsScale)
+              float4 *__restrict__ outP, float physicsScale, const int2 *__restrict__ baseFrom)
 {
     __shared__ int s_v[8], s_t[8];
     const int m = blockIdx.x, tid = threadIdx.x;
     int sv = 0, st = 0;
-    for (int i = tid; i < m; i += 256) { const int4 r = results[i]; sv += r.x; st += r.y; }
+    for (int i = tid; i < m; i += 256) { const int4 r = results[jobsByMesh[i].result]; sv += r.x; st += r.y; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); st += __shfl_xor_sync(0xffffffffu, st, o); }
     if ((tid & 31) == 0) { s_v[tid >> 5] = sv; s_t[tid >> 5] = st; }
     __syncthreads();
-    int baseV = 0, baseT = 0;
+    int baseV = baseFrom ? baseFrom->x : 0, baseT = baseFrom ? baseFrom->y : 0;
 #pragma unroll
     for (int q = 0; q < 8; q++) { baseV += s_v[q]; baseT += s_t[q]; }
     const SimpJobDev job = jobsByMesh[m];
-    const int4 r = results[m];
+    const int4 r = results[job.result];
     const float4 *src = reinterpret_cast<const float4 *>(V + job.vertexOffset);
     float4 *dst = reinterpret_cast<float4 *>(outV + baseV);
     if (outV) for (int i = tid; i < r.x * 3; i += 256) dst[i] = src[i];
@@ -741,7 +743,7 @@ k_pack_meshes(const SimpJobDev *__restrict__ jobsByMesh, const int4 *__restrict_
     int *td = outT + (size_t)baseT * 3;
     for (int i = tid; i < r.y * 3; i += 256) td[i] = ts[i];
     if (tid == 0) {
-        packedOffsets[m] = make_int2(baseV, baseT);
+        packedOffsets[job.result] = make_int2(baseV, baseT);
         if (m == numMeshes - 1) *totals = make_int2(baseV + r.x, baseT + r.y);
     }
 }
@@ -794,10 +796,19 @@ static int ensure_buffer(void **p, size_t *cap, size_t bytes)
 // With d_packT the simplified meshes are also gathered densely, in mesh order (vertices as MeshVertex
 // into d_packV and / or in the physics engine's format into d_packP, either may be null):
 // d_packOffsets[m] = (first vertex, first triangle), *d_packTotals = the totals.
+//
+// With `split` (and packing) the launch is cut in two.  A launch lasts as long as its largest mesh --
+// one block per mesh -- while most blocks are done in half that time.  The meshes with more than
+// half the triangles of the largest stay on `st` (the late group); the others run beside them on
+// split->streamB, are packed there first, at the front of the packed arrays, and
+// *split->d_earlyTotals says where their region ends: the caller can ship it while the late group is
+// still being simplified.  The late group is packed behind it on `st`.  Packed order is then: early
+// meshes in mesh order, late meshes in mesh order; d_packOffsets[m] addresses mesh m either way.
 int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int *d_T, int4 *d_results,
                     lvn_mesh_vertex *d_packV, int *d_packT, int2 *d_packOffsets, int2 *d_packTotals, cudaStream_t st,
-                    float4 *d_packP, float physicsScale)
+                    float4 *d_packP, float physicsScale, SimplifySplit *split)
 {
+    if (split) split->numEarly = 0;
     if (n <= 0) return LVN_SUCCESS;
     std::vector<SimpJobDev> jd(n);
     long long edgeTotal = 0, vtxTotal = 0;
@@ -869,6 +880,39 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     MCU(cudaMemsetAsync(d_timing, 0, sizeof(long long) * 16 * n, st));
     ws.timing = d_timing;
 #endif
+    // the late group = the front of the launch list (it is sorted by size)
+    int nLate = n;
+    if (split && d_packT && n >= 16 && !getenv("LVN_SIMP_NO_SPLIT")) {
+        nLate = 0;
+        static const int pct = getenv("LVN_SIMP_SPLIT_PCT") ? atoi(getenv("LVN_SIMP_SPLIT_PCT")) : 50;   // experiment switch
+        while (nLate < n && 100 * (long long)launch[nLate].numTriangles > (long long)pct * launch[0].numTriangles) nLate++;
+        if (nLate == 0 || nLate == n) nLate = n;
+    }
+    if (nLate < n) {
+        // pack lists in mesh order: the early group, then the late group
+        std::vector<char> late(n, 0);
+        for (int i = 0; i < nLate; i++) late[launch[i].result] = 1;
+        std::vector<SimpJobDev> lists;
+        lists.reserve(n);
+        for (int m = 0; m < n; m++) if (!late[m]) lists.push_back(jd[m]);
+        for (int m = 0; m < n; m++) if (late[m]) lists.push_back(jd[m]);
+        const int nEarly = n - nLate;
+        MCU(cudaMemcpyAsync(B + oJobs, lists.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
+        MCU(cudaEventRecord(split->evFork, st));
+        MCU(cudaStreamWaitEvent(split->streamB, split->evFork, 0));
+        const SimpJobDev *dl = (const SimpJobDev *)(B + oLaunch), *dj = (const SimpJobDev *)(B + oJobs);
+        k_simplify<<<nLate, SIMP_BLOCK, smem, st>>>(dl, ws, d_V, d_T, d_results);
+        k_simplify<<<nEarly, SIMP_BLOCK, smem, split->streamB>>>(dl + nLate, ws, d_V, d_T, d_results);
+        k_pack_meshes<<<nEarly, 256, 0, split->streamB>>>(dj, d_results, nEarly, d_V, d_T, d_packV, d_packT, d_packOffsets, split->d_earlyTotals,
+                                                          d_packP, physicsScale, nullptr);
+        MCU(cudaEventRecord(split->evEarly, split->streamB));
+        MCU(cudaStreamWaitEvent(st, split->evEarly, 0));
+        k_pack_meshes<<<nLate, 256, 0, st>>>(dj + nEarly, d_results, nLate, d_V, d_T, d_packV, d_packT, d_packOffsets, d_packTotals,
+                                             d_packP, physicsScale, split->d_earlyTotals);
+        MCU(cudaGetLastError());
+        split->numEarly = nEarly;
+        return LVN_SUCCESS;
+    }
     k_simplify<<<n, SIMP_BLOCK, smem, st>>>((const SimpJobDev *)(B + oLaunch), ws, d_V, d_T, d_results);
     MCU(cudaGetLastError());
 #ifdef LVN_SIMP_TIMING
@@ -886,7 +930,7 @@ int simplify_device(int n, const SimplifyMesh *meshes, lvn_mesh_vertex *d_V, int
     if (d_packT) {
         MCU(cudaMemcpyAsync(B + oJobs, jd.data(), sizeof(SimpJobDev) * n, cudaMemcpyHostToDevice, st));
         k_pack_meshes<<<n, 256, 0, st>>>((const SimpJobDev *)(B + oJobs), d_results, n, d_V, d_T, d_packV, d_packT, d_packOffsets, d_packTotals,
-                                         d_packP, physicsScale);
+                                         d_packP, physicsScale, nullptr);
         MCU(cudaGetLastError());
     }
     return LVN_SUCCESS;
@@ -930,7 +974,7 @@ extern "C" int lvn_mesh_simplify_batch(int numMeshes, const lvn_simplify_job *jo
     int4 *dRes = (int4 *)(IO + bV + bT);
     MCU(cudaMemcpyAsync(dV, vertices, sizeof(lvn_mesh_vertex) * (size_t)numVerticesTotal, cudaMemcpyHostToDevice, st));
     MCU(cudaMemcpyAsync(dT, triangles, 12 * (size_t)numTrianglesTotal, cudaMemcpyHostToDevice, st));
-    LV(simplify_device(numMeshes, meshes.data(), dV, dT, dRes, nullptr, nullptr, nullptr, nullptr, st, nullptr, 0.f));
+    LV(simplify_device(numMeshes, meshes.data(), dV, dT, dRes, nullptr, nullptr, nullptr, nullptr, st, nullptr, 0.f, nullptr));
     std::vector<int4> res(numMeshes);
     MCU(cudaMemcpyAsync(res.data(), dRes, sizeof(int4) * numMeshes, cudaMemcpyDeviceToHost, st));
     // the simplified meshes stay in their input slots (a mesh never grows): two copies back
