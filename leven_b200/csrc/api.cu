@@ -1262,7 +1262,7 @@ int lvn::generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunk
         const int rc = simplify_device(M, meshes.data(), ctx->d_vertices.p, ctx->d_tris.p, ctx->d_simpRes.p,
                                        vertices ? ctx->d_packV.p : nullptr, ctx->d_packT.p, ctx->d_packOff.p, ctx->d_packOff.p + M, st,
                                        physicsVertices ? ctx->d_packP.p : nullptr, physicsScale,
-                                       deferMeshCopies ? nullptr : &split);   // (a caller that defers overlaps the download itself)
+                                       (deferMeshCopies && !getenv("LVN_SIMP_SPLIT_DEFER")) ? nullptr : &split);   // (a caller that defers overlaps the download itself)
         if (rc < 0) { g_lastCudaError = simplify_last_error(); return rc; }
         CU(cudaMemcpyAsync(ctx->h_simpRes.p, ctx->d_simpRes.p, sizeof(int4) * M, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ctx->h_packOff.p, ctx->d_packOff.p, sizeof(int2) * ((size_t)M + 1), cudaMemcpyDeviceToHost, st));

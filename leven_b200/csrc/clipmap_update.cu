@@ -12,8 +12,11 @@
 // the cell's min or its min lies inside the cell (AABB::pointIsInside, aabb.h:37-43).  Octree cells
 // are aligned, so the reference's tree descent prunes nothing this flat test keeps.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
+#include <chrono>
 #include <vector>
 
 #include "lvn_internal.h"
@@ -71,6 +74,11 @@ struct ActiveIndex {
 
 }  // namespace
 
+// LVN_UPDATE_TIMING=1: host wall-clock of the update's phases on stderr (no extra synchronisation)
+static bool update_timing() { static const bool on = getenv("LVN_UPDATE_TIMING") && atoi(getenv("LVN_UPDATE_TIMING")) != 0; return on; }
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+
 // Pass 2 on its own: the seam-update set of an update (clipmap.cpp:1306-1324) over the nodes listed in
 // `active`, and GenerateClipmapSeamMesh (clipmap.cpp:573-611) for the share of that set this caller
 // takes: entry u of the (ascending) set belongs to shard u % shardCount.  With one GPU the share is
@@ -88,6 +96,7 @@ extern "C" int lvn_clipmap_seam_update_batch(int voxelsPerChunk, const lvn_clipm
         !numSeamUpdatesAll || !numSeamUpdatesMine || (numActive > 0 && (!nodes || !active)) || (numConstructed > 0 && !constructed))
         return LVN_ERR_INVALID_VALUE;
     *numSeamUpdatesAll = 0; *numSeamUpdatesMine = 0;
+    const double tEnter = now_us();
     std::vector<int> act(active, active + numActive);
     for (int a : act) if (a < 0 || a >= numNodes) return LVN_ERR_INVALID_VALUE;
     for (int c = 0; c < numConstructed; c++) if (constructed[c] < 0 || constructed[c] >= numNodes) return LVN_ERR_INVALID_VALUE;
@@ -145,8 +154,12 @@ extern "C" int lvn_clipmap_seam_update_batch(int voxelsPerChunk, const lvn_clipm
         }
         j.numNeighbours = (int32_t)nbs.size() - j.firstNeighbour;
     }
-    return lvn_seam_mesh_generate_batch(voxelsPerChunk, (int)jobs.size(), jobs.data(), nbs.data(), (int)nbs.size(), seamNodes, (int)numSeamNodes,
-                                        vertices, vertexCapacity, triangles, triangleCapacity, seamResults);
+    const double tJobs = now_us();
+    const int rc = lvn_seam_mesh_generate_batch(voxelsPerChunk, (int)jobs.size(), jobs.data(), nbs.data(), (int)nbs.size(), seamNodes, (int)numSeamNodes,
+                                                vertices, vertexCapacity, triangles, triangleCapacity, seamResults);
+    if (update_timing())
+        fprintf(stderr, "[lvn update]   pass 2: seam-update set + job lists on the host %.0f us, seam batch %.0f us\n", tJobs - tEnter, now_us() - tJobs);
+    return rc;
 }
 
 extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *nodes, int numActive, int numConstruct,
@@ -173,6 +186,7 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
             return LVN_ERR_INVALID_VALUE;
     }
 
+    const double tStart = now_us();
     // ---- 1. construct (clipmap.cpp:1253-1282) ----
     lvn_clipmap_node *construct = nodes + numActive;
     if (numConstruct > 0) {
@@ -209,6 +223,7 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
         }
     totals->numConstructedActive = (int32_t)constructed.size();
 
+    const double tPass1 = now_us();
     // ---- 2 + 3. the seam-update set and its seam meshes, after the node meshes in the two arenas ----
     int32_t numMine = 0;
     const int rc = lvn_clipmap_seam_update_batch(V, nodes, numActive + numConstruct, active.data(), (int)active.size(),
@@ -222,6 +237,10 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
         r.vertexOffset += (int32_t)totals->nodeVertices;
         r.triangleOffset += (int32_t)totals->nodeTriangles;
     }
+    const double tPass2 = now_us();
     const int rcWait = lvn::meshgen_wait(ctx);
+    if (update_timing())
+        fprintf(stderr, "[lvn update] pass 1 (construct, node meshes still in flight) %.0f us, pass 2 (seam set + seam meshes) %.0f us, wait for the node meshes %.0f us\n",
+                tPass1 - tStart, tPass2 - tPass1, now_us() - tPass2);
     return rc < 0 ? rc : rcWait;
 }
