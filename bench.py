@@ -315,6 +315,19 @@ def main():
         step_e2e()
     e2e_ms, e2e_wall = timed_region(step_e2e, args.steps)
     pipe_e2e = ctx.getPipeline()
+    # the link itself on this box: the step's download as one device -> pinned-host copy (outside the
+    # timed regions; boxes of one pool differ here, and the end-to-end step is bound by it)
+    link_bytes = (totV * lc.MeshVertex.itemsize + totT * lc.MeshTriangle.itemsize + totS * lc.SeamNodeInfo.itemsize)
+    link_host = torch.empty(link_bytes, dtype=torch.uint8, pin_memory=True)
+    link_ms = []
+    for _ in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        link_host.copy_(flush[:link_bytes], non_blocking=True)
+        b.record(stream)
+        torch.cuda.synchronize()
+        link_ms.append(a.elapsed_time(b))
+    link_ms = float(np.median(link_ms[2:]))
     sampler.mark()
     clocks = sampler.stop()
     # ---- per-kernel durations: the same step with one lane on one stream, so that every kernel
@@ -410,6 +423,8 @@ def main():
         "ms_per_step_wall_incl_flush": 1e3 * wall / args.steps,
         "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / args.steps,
+                "link": {"d2h_copy_ms": link_ms, "gbs": link_bytes / link_ms / 1e6, "frac_of_step": link_ms / (e2e_ms_max / args.steps),
+                         "what": "the step's download as ONE device -> pinned host copy on rank 0's box, timed alone: the PCIe floor of the step"},
                 "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)"},
         "gpu_launches": int(sum(run_stats["launches"].values())),
         "clocks": clocks,
