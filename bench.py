@@ -320,6 +320,7 @@ def main():
     link_bytes = (totV * lc.MeshVertex.itemsize + totT * lc.MeshTriangle.itemsize + totS * lc.SeamNodeInfo.itemsize)
     link_host = torch.empty(link_bytes, dtype=torch.uint8, pin_memory=True)
     link_ms = []
+    barrier()          # every rank copies at the same time: the ranks of one box share its host side
     for _ in range(7):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
@@ -424,7 +425,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / args.steps,
                 "link": {"d2h_copy_ms": link_ms, "gbs": link_bytes / link_ms / 1e6, "frac_of_step": link_ms / (e2e_ms_max / args.steps),
-                         "what": "the step's download as ONE device -> pinned host copy on rank 0's box, timed alone: the PCIe floor of the step"},
+                         "what": "the step's download as ONE device -> pinned host copy, no kernels running, all ranks copying at the same "
+                                 "time (rank 0's figure): the PCIe floor of the step on this box at this number of GPUs"},
                 "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)"},
         "gpu_launches": int(sum(run_stats["launches"].values())),
         "clocks": clocks,
