@@ -344,6 +344,12 @@ def main():
     dev_ms_max = max_over_ranks(dev_ms)
     e2e_ms_max = max_over_ranks(e2e_ms)
     total_chunks = sum_over_ranks(nchunks) * args.steps
+    # every rank's own figures (rank order): end-to-end ms per step, device-resident ms per step, link GB/s
+    mine = torch.tensor([e2e_ms / args.steps, dev_ms / args.steps, link_bytes / link_ms / 1e6], device=dev, dtype=torch.float64)
+    per_rank = [mine.clone() for _ in range(world_size)]
+    if world_size > 1:
+        dist.all_gather(per_rank, mine)
+    per_rank = [[round(float(v), 4) for v in t.tolist()] for t in per_rank]
     value = total_chunks / (dev_ms_max * 1e-3)
     e2e_value = total_chunks / (e2e_ms_max * 1e-3)
 
@@ -428,6 +434,8 @@ def main():
                          "what": "the step's download as ONE device -> pinned host copy, no kernels running, all ranks copying at the same "
                                  "time (rank 0's figure): the PCIe floor of the step on this box at this number of GPUs"},
                 "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)"},
+        "per_rank": {"e2e_ms_per_step": [r[0] for r in per_rank], "device_ms_per_step": [r[1] for r in per_rank],
+                     "link_gbs": [r[2] for r in per_rank]},
         "gpu_launches": int(sum(run_stats["launches"].values())),
         "clocks": clocks,
         "roofline": {"kernel": "k_hermite (FindEdgeIntersectionInfo)", "bound": "fp32",
