@@ -19,6 +19,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <random>
 #include <string>
@@ -771,6 +772,8 @@ static void choose_pipeline(const lvn_meshgen *ctx, int n, const BatchOpts &opts
     streams = lanes == 1 ? 1 : std::max(1, std::min(std::min(streams, LVN_MAX_STREAMS), lanes));
 }
 
+static double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // every stream a lane ran on, and the copy stream, rejoin the context's stream
 static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies)
 {
@@ -799,6 +802,8 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     const Dims &d = ctx->dims;
     const size_t FF = (size_t)d.F * d.F, HH = (size_t)d.H * d.H, VV = (size_t)d.V * d.V, F3 = FF * d.F;
     cudaStream_t st = ctx->stream;
+    const double hostStart = ctx->trace ? host_now_us() : 0.0;   // LVN_TRACE: where the host thread's time goes
+    double hostWaited = 0.0;
     ctx->lastN = n;
     ctx->numLanes = 0;
     ctx->hostLayout = false;
@@ -1042,8 +1047,10 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             for (int k = 0; k < S; k++) {
                 while (issued < S && issued < k + 2) LV(enqueue_lane(issued++));
                 if (overflow || hostFull) continue;   // keep issuing: the retry needs every lane's counts
+                const double w0 = ctx->trace ? host_now_us() : 0.0;
                 if (S > 1) CU(cudaEventSynchronize(ctx->evPub[k]));
                 else CU(cudaStreamSynchronize(st));
+                if (ctx->trace) hostWaited += host_now_us() - w0;
                 const ArenaCounters c = *lane_counters_host(k);
                 if (c.overflow) { overflow = true; continue; }
                 ctx->hostBase[k][0] = hv; ctx->hostBase[k][1] = ht; ctx->hostBase[k][2] = hs;
@@ -1080,7 +1087,13 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             }
         }
 #undef LVN_TRACE_EV
+        const double j0 = ctx->trace ? host_now_us() : 0.0;
         LV(join_lanes(ctx, R, out != nullptr && S > 1));
+        if (ctx->trace) {
+            hostWaited += host_now_us() - j0;
+            fprintf(stderr, "[lvn trace] host thread: %.0f us in the call, %.0f us of them waiting for the GPU (the rest: building the batch, driver calls)\n",
+                    host_now_us() - hostStart, hostWaited);
+        }
         CU(cudaGetLastError());
         collect_stage_times(ctx);
         if (ctx->trace) {
