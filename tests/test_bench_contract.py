@@ -30,3 +30,14 @@ def test_reference_arm_line(built):
 def test_reference_arm_other_ranks_are_silent(built):
     p = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_cuda_arm_refuses_without_a_device(built):
+    """the CUDA arm has no CPU fallback: without a device it says so and exits non-zero"""
+    import torch
+    if torch.cuda.is_available():
+        return
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout) and not p.stdout.strip().startswith("{")
