@@ -393,7 +393,9 @@ def main():
          "executed_flop": col_sets * F2 * FLOP_PER_DENSITY,
          "achieved_tflops": col_sets * F2 * FLOP_PER_DENSITY / (stage_ms["columns"] * 1e-3) / 1e12
          if stage_ms["columns"] > 0 else 0.0,
-         "peak_tflops": fp32_peak},
+         "peak_tflops": fp32_peak,
+         "note": "this interval starts when the copy engine has delivered the batch head and so includes the hand-over to the "
+                 "compute engine; the kernel alone takes 14 us (ncu, profiles/r01t_summary.txt), 0.33 of the peak on its executed flops"},
         {"stage": "rows (S2+S4)", "bound": "hbm", "ms": stage_ms["classify"], "algorithmic_bytes": classify_bytes,
          "achieved_gbs": gbs(classify_bytes, stage_ms["classify"]), "peak_gbs": hbm_peak},
         {"stage": "hermite (S3)", "bound": "fp32", "ms": stage_ms["hermite"], "algorithmic_flop": herm_flop,
