@@ -182,3 +182,47 @@ def test_gpu_sharded_update_pieces(lc, surface_cy, built):
                                T3["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]]) == whole[int(k)]
     finally:
         ctx.destroy()
+
+
+def _random_cover(rng, depth=2):
+    """an octree cover of a 2048^3 cube: cells split at random down to 256 (aligned, non-overlapping)"""
+    cells = [((0, 0, 0), 2048)]
+    out = []
+    while cells:
+        mn, size = cells.pop()
+        if size > 256 and (size > 1024 or rng.random() < 0.55):
+            h = size // 2
+            cells += [((mn[0] + dx * h, mn[1] + dy * h, mn[2] + dz * h), h) for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)]
+        else:
+            out.append((mn, size))
+    return out
+
+
+def test_seam_update_set_host_logic_random_covers(built):
+    """the seam-update set (clipmap.cpp:1306-1324) is host logic: on random mixed-LOD covers with a
+    random part of the nodes newly constructed it equals the brute-force statement of the rule, is
+    ascending, and its shares partition it (no device needed: the set is reported before the seam
+    launch is attempted)"""
+    import torch
+    import leven_b200.compute as lc          # (not the `lc` fixture: that one needs a device)
+    rng = np.random.default_rng(31)
+    for trial in range(12):
+        cover = [c for c in _random_cover(rng) if rng.random() < 0.8]        # some cells stay empty / inactive
+        nodes = np.zeros(len(cover), lc.ClipmapNode)
+        for k, (mn, size) in enumerate(cover):
+            nodes[k]["min"] = mn; nodes[k]["size"] = size
+        nodes["numSeamNodes"] = 1
+        active = np.arange(len(cover), dtype=np.int32)
+        constructed = np.sort(rng.choice(len(cover), size=max(1, len(cover) // 5), replace=False)).astype(np.int32)
+        want = brute_force_updates(cover, [cover[i] for i in constructed])
+        want_idx = sorted(k for k, c in enumerate(cover) if (tuple(c[0]), c[1]) in want)
+        V = np.zeros(8, lc.MeshVertex); T = np.zeros(8, lc.MeshTriangle); arena = np.zeros(8, lc.SeamNodeInfo)
+        got = []
+        for shard in range(3):
+            rc, upd, sres, n_all = lc.ClipmapSeamUpdateBatch(64, nodes, active, constructed, arena, 8, V, T, shard, 3)
+            if not torch.cuda.is_available():
+                assert rc == lc.LVN_ERR_NO_DEVICE or len(upd) == 0
+            assert n_all == len(want_idx), (trial, n_all, len(want_idx))
+            assert upd.tolist() == want_idx[shard::3]
+            got += upd.tolist()
+        assert sorted(got) == want_idx and len(want_idx) >= len(constructed)
