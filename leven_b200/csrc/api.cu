@@ -1067,7 +1067,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 if (c.nodes) { dst[m] = out->vertices + hv; src[m] = ctx->d_vertices.p + b.nodes; len[m++] = (size_t)c.nodes * sizeof(lvn_mesh_vertex); }
                 if (c.quads) { dst[m] = out->triangles + ht; src[m] = ctx->d_tris.p + (size_t)b.quads * 6; len[m++] = (size_t)c.quads * 6 * sizeof(int); }
                 if (c.seams) { dst[m] = out->seams + hs; src[m] = ctx->d_seams.p + b.seams; len[m++] = (size_t)c.seams * sizeof(lvn_seam_node_info); }
-#if CUDART_VERSION >= 12080
+#if CUDART_VERSION >= 12080 && CUDART_VERSION < 13000   // the 12.8 / 12.9 signature (size_t *failIdx); plain copies otherwise
                 // (small single-lane batches usually land in pageable memory, where the batched call
                 // costs ~0.6 ms more than three plain copies: measured with config 3's re-meshes)
                 if (m > 1 && S > 1) {
@@ -1175,10 +1175,25 @@ static void fill_results(lvn_meshgen *ctx, int n, lvn_chunk_result *results)
     (void)n;
 }
 
+static int load_density_fields(lvn_meshgen *ctx, int n, const int32_t *minSize, bool forceEntry, bool withTables,
+                               std::vector<FieldEntry *> &out);
+
+// LoadDensityField's replay (compute_density_field.cpp:235-274) for the batch entry points: every
+// generateChunkMesh of the reference passes through it, so a chunk that stored operations
+// overlap is meshed from the edited field, whichever entry point asks.  Without stored
+// operations this is one test.
+static int replay_stored_ops(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize)
+{
+    if (!g.initialised || !ctx || n <= 0 || !chunkMinSize || g.storedOps.empty()) return LVN_SUCCESS;
+    std::vector<FieldEntry *> entries;
+    return load_density_fields(ctx, n, chunkMinSize, false, true, entries);
+}
+
 extern "C" int lvn_meshgen_generate_batch_device(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
                                                  lvn_chunk_result *results, lvn_batch_device_view *view)
 {
     BatchOpts opts;
+    LV(replay_stored_ops(ctx, nChunks, chunkMinSize));
     LV(run_batch(ctx, nChunks, chunkMinSize, opts));
     if (results) fill_results(ctx, nChunks, results);
     if (view) {
@@ -1203,6 +1218,7 @@ extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const i
     if (!results) return LVN_ERR_INVALID_VALUE;
     BatchOpts opts;
     HostOut out = {vertices, vertexCapacity, triangles, triangleCapacity, seamNodes, seamCapacity};
+    LV(replay_stored_ops(ctx, nChunks, chunkMinSize));
     const int rc = run_batch(ctx, nChunks, chunkMinSize, opts, &out);
     if (rc == LVN_SUCCESS || rc == LVN_ERR_CAPACITY) {
         // on LVN_ERR_CAPACITY the counts say what the caller must provide
@@ -1222,10 +1238,12 @@ int lvn::generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunk
                              lvn_mesh_vertex *vertices, float *physicsVertices, float physicsScale, int64_t vertexCapacity,
                              lvn_mesh_triangle *triangles, int64_t triangleCapacity,
                              lvn_seam_node_info *seamNodes, int64_t seamCapacity,
-                             lvn_chunk_result *results, lvn_simplify_result *simplified, bool deferMeshCopies)
+                             lvn_chunk_result *results, lvn_simplify_result *simplified, bool deferMeshCopies,
+                             uint8_t *hadMesh)
 {
     if (!results || !unitOptions) return LVN_ERR_INVALID_VALUE;
     BatchOpts opts;
+    LV(replay_stored_ops(ctx, nChunks, chunkMinSize));
     LV(run_batch(ctx, nChunks, chunkMinSize, opts));
     if (nChunks == 0) return LVN_SUCCESS;
     fill_results(ctx, nChunks, results);      // offsets into the device arenas
@@ -1237,6 +1255,7 @@ int lvn::generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunk
     for (int i = 0; i < nChunks; i++) {
         const lvn_chunk_result &r = results[i];
         if (simplified) simplified[i] = lvn_simplify_result{0, 0, 0, 0};
+        if (hadMesh) hadMesh[i] = r.status >= 0 && r.numTriangles > 0;   // renderMesh != null before ngMeshSimplifier (clipmap.cpp:466)
         if (r.status < 0 || r.numTriangles <= 0) continue;
         const int32_t *ms = chunkMinSize + 4 * (size_t)i;
         SimplifyMesh m;
@@ -1349,7 +1368,7 @@ extern "C" int lvn_meshgen_generate_simplified_batch(lvn_meshgen *ctx, int nChun
                                                      lvn_chunk_result *results, lvn_simplify_result *simplified)
 {
     return generate_simplified(ctx, nChunks, chunkMinSize, unitOptions, vertices, nullptr, 0.f, vertexCapacity, triangles, triangleCapacity,
-                               seamNodes, seamCapacity, results, simplified, false);
+                               seamNodes, seamCapacity, results, simplified, false, nullptr);
 }
 
 // Clipmap::loadCollisionNodes' per-node work (clipmap.cpp:1346-1385): ConstructCollisionNodeData, then the
@@ -1363,7 +1382,7 @@ extern "C" int lvn_meshgen_generate_collision_batch(lvn_meshgen *ctx, int nNodes
 {
     if (!physicsVertices && !vertices && vertexCapacity > 0) return LVN_ERR_INVALID_VALUE;
     return generate_simplified(ctx, nNodes, nodeMinSize, unitOptions, vertices, physicsVertices, physicsScale, vertexCapacity,
-                               (lvn_mesh_triangle *)triangles, triangleCapacity, seamNodes, seamCapacity, results, simplified, false);
+                               (lvn_mesh_triangle *)triangles, triangleCapacity, seamNodes, seamCapacity, results, simplified, false, nullptr);
 }
 
 // ---------------------------------------------------------------------------

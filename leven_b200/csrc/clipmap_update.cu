@@ -189,6 +189,7 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
     const double tStart = now_us();
     // ---- 1. construct (clipmap.cpp:1253-1282) ----
     lvn_clipmap_node *construct = nodes + numActive;
+    std::vector<uint8_t> hadMesh((size_t)std::max(numConstruct, 1), 0);
     if (numConstruct > 0) {
         std::vector<int32_t> minSize(4 * (size_t)numConstruct);
         for (int i = 0; i < numConstruct; i++) {
@@ -198,7 +199,7 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
         // (the node meshes are still on their way to the host arenas while pass 2 runs: it needs the seam nodes only)
         const int rc = lvn::generate_simplified(ctx, numConstruct, minSize.data(), unitOptions, vertices, nullptr, 0.f, vertexCapacity,
                                                 triangles, triangleCapacity, seamNodes ? seamNodes + seamNodesUsed : nullptr,
-                                                seamCapacity - seamNodesUsed, constructResults, nullptr, true);
+                                                seamCapacity - seamNodesUsed, constructResults, nullptr, true, hadMesh.data());
         int64_t sn = 0;
         for (int i = 0; i < numConstruct; i++) {
             const lvn_chunk_result &r = constructResults[i];
@@ -213,11 +214,14 @@ extern "C" int lvn_clipmap_update_batch(lvn_meshgen *ctx, lvn_clipmap_node *node
             construct[i].numSeamNodes = r.numSeamNodes;
         }
     }
-    // a node with a mesh or seam nodes becomes active, the others are empty (clipmap.cpp:1269-1281)
+    // a node with a mesh buffer (decided before the simplifier runs, clipmap.cpp:446-466) or seam nodes
+    // becomes active, the others are empty (clipmap.cpp:1269-1281).  Active nodes never nest: the
+    // reference's FindActiveNodes stops at the first active node on its way down, the flat cell test
+    // would report both an active ancestor and its active descendant.
     std::vector<int> active, constructed;
     for (int i = 0; i < numActive; i++) active.push_back(i);
     for (int i = 0; i < numConstruct; i++)
-        if (constructResults[i].numTriangles > 0 || constructResults[i].numSeamNodes > 0) {
+        if (hadMesh[i] || constructResults[i].numSeamNodes > 0) {
             active.push_back(numActive + i);
             constructed.push_back(numActive + i);
         }

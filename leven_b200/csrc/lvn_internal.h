@@ -199,7 +199,8 @@ const char *simplify_last_error();
 int generate_simplified(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize, const lvn_simplify_options *unitOptions,
                         lvn_mesh_vertex *vertices, float *physicsVertices, float physicsScale, int64_t vertexCapacity,
                         lvn_mesh_triangle *triangles, int64_t triangleCapacity, lvn_seam_node_info *seamNodes, int64_t seamCapacity,
-                        lvn_chunk_result *results, lvn_simplify_result *simplified, bool deferMeshCopies);
+                        lvn_chunk_result *results, lvn_simplify_result *simplified, bool deferMeshCopies,
+                        uint8_t *hadMesh);   // hadMesh (optional): chunk i had a mesh before the simplifier ran
 int meshgen_wait(lvn_meshgen *ctx);
 
 }  // namespace lvn

@@ -1762,3 +1762,61 @@ int lvo_generate_batch_counts(const lvo_world *w, int n, const int *minSize, int
     }
     return threads;
 }
+
+/* FNV-1a over a byte range: the per-chunk digests of lvo_generate_batch_digests (test
+ * infrastructure: lets the full-size configurations be compared chunk by chunk without
+ * holding every reference mesh in memory) */
+static uint64_t fnv1a64(const void *data, size_t bytes)
+{
+    const uint8_t *p = (const uint8_t *)data;
+    uint64_t h = 1469598103934665603ull;
+    size_t i;
+    for (i = 0; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+uint64_t lvo_fnv1a64(const void *data, size_t bytes) { return fnv1a64(data, bytes); }
+
+/* Like lvo_generate_batch_counts, and additionally digests[3*i..] = FNV-1a of chunk i's vertex
+ * buffer (numNodes * 48 B), triangle indices in order (T * 12 B) and seam nodes (S * 48 B) --
+ * the three arrays generateChunkMesh hands out (compute_octree.cpp:326-347, :275-322). */
+int lvo_generate_batch_digests(const lvo_world *w, int n, const int *minSize, int32_t *counts, uint64_t *digests)
+{
+    int i, threads = 1;
+#ifdef _OPENMP
+    threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (i = 0; i < n; i++) {
+        const int *ms = &minSize[4 * i];
+        lvo_field field;
+        lvo_octree octree;
+        int T = 0, S = 0;
+        generate_default(w, ms, ms[3], &field);
+        memset(&octree, 0, sizeof(octree));
+        digests[3 * i + 0] = digests[3 * i + 1] = digests[3 * i + 2] = fnv1a64(NULL, 0);
+        if (field.numEdges > 0) {
+            construct_octree(w, ms, &field, &octree);
+            if (octree.numNodes > 0) {
+                int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * 18 * (size_t)octree.numNodes);
+                lvo_vertex *vb = (lvo_vertex *)malloc(sizeof(lvo_vertex) * (size_t)octree.numNodes);
+                lvo_seam_node *sn = (lvo_seam_node *)malloc(sizeof(lvo_seam_node) * (size_t)octree.numNodes);
+                T = lvo_generate_mesh(w, octree.codes, octree.matWords, octree.numNodes, idx);
+                lvo_vertex_buffer(octree.positions, octree.normals, octree.matWords, octree.numNodes, ms[3], vb);
+                S = lvo_seam_nodes(w, octree.codes, octree.matWords, octree.positions, octree.normals,
+                                   octree.numNodes, sn);
+                digests[3 * i + 0] = fnv1a64(vb, sizeof(lvo_vertex) * (size_t)octree.numNodes);
+                digests[3 * i + 1] = fnv1a64(idx, sizeof(int32_t) * 3 * (size_t)T);
+                digests[3 * i + 2] = fnv1a64(sn, sizeof(lvo_seam_node) * (size_t)S);
+                free(idx); free(vb); free(sn);
+            }
+        }
+        counts[4 * i + 0] = field.numEdges;
+        counts[4 * i + 1] = octree.numNodes;
+        counts[4 * i + 2] = T;
+        counts[4 * i + 3] = S;
+        field_release(&field);
+        octree_release(&octree);
+    }
+    return threads;
+}

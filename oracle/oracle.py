@@ -102,6 +102,8 @@ def lib():
         L.lvo_chunk_free.argtypes = [P]
         L.lvo_generate_batch_counts.argtypes = [P, I, P, P]; L.lvo_generate_batch_counts.restype = I
         L.lvo_set_num_threads.argtypes = [I]; L.lvo_set_num_threads.restype = I
+        L.lvo_generate_batch_digests.argtypes = [P, I, P, P, P]; L.lvo_generate_batch_digests.restype = I
+        L.lvo_fnv1a64.argtypes = [P, C.c_size_t]; L.lvo_fnv1a64.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -236,11 +238,26 @@ class World:
         self.L.lvo_is_chunk_empty(self.h, _i3(mn), int(size), C.byref(e))
         return bool(e.value)
 
+    def batch_digests(self, min_size):
+        """counts (E, N, T, S) and FNV-1a digests (vertices, indices, seam nodes) per chunk, OpenMP over chunks"""
+        ms = np.ascontiguousarray(min_size, np.int32).reshape(-1, 4)
+        counts = np.zeros((len(ms), 4), np.int32)
+        digests = np.zeros((len(ms), 3), np.uint64)
+        self.L.lvo_generate_batch_digests(self.h, len(ms), _ptr(ms), _ptr(counts), _ptr(digests))
+        return counts, digests
+
     def batch_counts(self, min_size):
         ms = np.ascontiguousarray(min_size, np.int32).reshape(-1, 4)
         counts = np.zeros((len(ms), 4), np.int32)
         threads = self.L.lvo_generate_batch_counts(self.h, len(ms), _ptr(ms), _ptr(counts))
         return counts, threads
+
+
+def fnv1a64(data):
+    """FNV-1a 64 of an array's bytes: the digest lvo_generate_batch_digests takes of each chunk's
+    arrays, applied by the tests to the CUDA path's output"""
+    b = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    return int(lib().lvo_fnv1a64(_ptr(b) if len(b) else None, len(b)))
 
 
 def csg_operation_bounds(op):
