@@ -58,6 +58,48 @@ def gather_global_offsets(local_counts, local_indices, num_chunks, group=None):
     return counts.numpy(), offsets.numpy(), counts.sum(dim=0).numpy()
 
 
+class CountGather:
+    """gather_global_offsets for a step that repeats: the buffers (pinned host staging + one device
+    tensor per direction with NCCL; plain CPU tensors with gloo / one rank) are allocated once and a
+    gather is one all_gather of exactly 12 B per chunk.  Round-robin sharding (chunk i on rank
+    i mod G) makes the gathered array [G][ceil(n / G)][3] the transpose of the linear order.
+
+    gather(numVertices, numTriangles, numSeamNodes) -> (counts[n, 3], offsets[n, 3], totals[3]),
+    identical on every rank."""
+
+    def __init__(self, num_chunks, rank, world_size, device=None, group=None):
+        import torch
+        self.torch, self.n, self.rank, self.world, self.group = torch, int(num_chunks), int(rank), int(world_size), group
+        self.per = (self.n + self.world - 1) // self.world
+        self.mine = len(shard_round_robin(self.n, self.rank, self.world))
+        self.device = device
+        on_gpu = device is not None
+        self.h_in = torch.zeros((self.per, 3), dtype=torch.int32, pin_memory=on_gpu)
+        self.h_out = torch.zeros((self.world, self.per, 3), dtype=torch.int32, pin_memory=on_gpu)
+        if on_gpu:
+            self.d_in = torch.zeros((self.per, 3), dtype=torch.int32, device=device)
+            self.d_out = torch.zeros((self.world, self.per, 3), dtype=torch.int32, device=device)
+
+    def gather(self, num_vertices, num_triangles, num_seam_nodes):
+        torch = self.torch
+        import torch.distributed as dist
+        a = self.h_in.numpy()
+        a[:self.mine, 0] = num_vertices; a[:self.mine, 1] = num_triangles; a[:self.mine, 2] = num_seam_nodes
+        multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        if not multi:
+            self.h_out[0].copy_(self.h_in)
+        elif self.device is not None:
+            self.d_in.copy_(self.h_in, non_blocking=True)
+            dist.all_gather_into_tensor(self.d_out.view(-1), self.d_in.view(-1), group=self.group)
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            dist.all_gather_into_tensor(self.h_out.view(-1), self.h_in.view(-1), group=self.group)
+        counts = self.h_out.numpy().transpose(1, 0, 2).reshape(-1, 3)[:self.n].astype(np.int64)
+        offsets = np.cumsum(counts, axis=0) - counts
+        return counts, offsets, counts.sum(axis=0)
+
+
 # ---------------------------------------------------------------------------------------------
 # The batched Clipmap::update over G GPUs (DESIGN.md 9).  Pass 1 -- constructing nodes -- shards
 # like the chunk path: node i of the list goes to GPU i mod G, no exchange.  Pass 2 -- the seam
