@@ -280,10 +280,14 @@ def stage_table(stats, K, nchunks, col_sets, kind, fp32_peak, hbm_peak, prof=Non
     stages.append({"stage": "hermite (S3)", "kernel": "k_hermite_terrain" if kind == "terrain" else "k_hermite_density",
                    "bound": "fp32", "ms": ms["hermite"], "algorithmic_flop": herm_flop, "algorithmic": herm_note,
                    "achieved_tflops": tfl(herm_flop, ms["hermite"]), "peak_tflops": fp32_peak})
-    leaves_bytes = (8 * N + 20 * E + 32 * N) + (8 * N + 72 * N + 24 * Q) + (36 * N + 48 * N) + (4 * N + 36 * S + 48 * S)
-    stages.append({"stage": "leaves (S5+S6+S8+S9+S10)", "kernel": "k_leaves", "bound": "hbm", "ms": ms["leaves"],
-                   "algorithmic_bytes": leaves_bytes, "achieved_gbs": gbs(leaves_bytes, ms["leaves"]), "peak_gbs": hbm_peak,
-                   "solve_flop": 1670 * N, "solve_tflops": tfl(1670 * N, ms["leaves"])})
+    # S5 (unfused: 8N + 20E read, 80N written) + S8 + S9 + S10 for k_leaves; S6 for k_solve
+    leaves_bytes = (8 * N + 20 * E + 80 * N) + (8 * N + 72 * N + 24 * Q) + (36 * N + 48 * N) + (4 * N + 36 * S + 48 * S)
+    stages.append({"stage": "leaves (S5+S8+S9+S10)", "kernel": "k_leaves", "bound": "hbm", "ms": ms["leaves"],
+                   "algorithmic_bytes": leaves_bytes, "achieved_gbs": gbs(leaves_bytes, ms["leaves"]), "peak_gbs": hbm_peak})
+    stages.append({"stage": "solve (S6)", "kernel": "k_solve", "bound": "fp32", "ms": ms["solve"],
+                   "algorithmic_flop": 1670 * N, "algorithmic": "1670 flop per node (SURVEY.md 8d); read 64N, write 16N B",
+                   "achieved_tflops": tfl(1670 * N, ms["solve"]), "peak_tflops": fp32_peak,
+                   "algorithmic_bytes": 80 * N, "achieved_gbs": gbs(80 * N, ms["solve"])})
     issue_peak = 4 * 148 * (sm_mhz or 1965.0) * 1e6
     for s in stages:
         if s["bound"] == "fp32":

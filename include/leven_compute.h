@@ -192,10 +192,11 @@ enum {
     LVN_STAGE_COLUMNS = 0,   /* S1 density: Terrain per column (noise.cl:205-223) */
     LVN_STAGE_CLASSIFY,      /* S2+S4 edge scan, active voxels, prefix sums, compaction */
     LVN_STAGE_HERMITE,       /* S3 FindEdgeIntersectionInfo (density_field.cl:96-151) */
-    LVN_STAGE_LEAVES,        /* S5+S6+S8+S9+S10 leaf QEF + solve + mesh + seams */
+    LVN_STAGE_LEAVES,        /* S5+S8+S9+S10 leaf QEF accumulation + mesh + seams (k_leaves) */
     LVN_STAGE_FIELD,         /* u8 material field materialisation (CSG / 3-D density) */
     LVN_STAGE_CSG,           /* a16 kernels */
     LVN_STAGE_CUCKOO,        /* a9 kernels */
+    LVN_STAGE_SOLVE,         /* S6 SolveQEFs (k_solve) */
     LVN_NUM_STAGES
 };
 typedef struct lvn_stage_stats {
@@ -382,6 +383,15 @@ int lvn_clipmap_seam_update_batch(int voxelsPerChunk, const lvn_clipmap_node *no
                                   lvn_mesh_triangle *triangles, int64_t triangleCapacity,
                                   int32_t *seamUpdateNodes, lvn_seam_result *seamResults, const float seamColour[3],
                                   int32_t *numSeamUpdatesAll, int32_t *numSeamUpdatesMine);
+
+/* new: placing the chunks of a sharded batch in one global mesh ("only a final count /
+ * size gather where a global mesh is assembled").  gathered = the all-gathered per-chunk counts of a
+ * round-robin split, [worldSize][3][perRank] (plane 0 vertices, 1 triangles, 2 seam nodes; chunk i of
+ * the linear order sits at rank i % worldSize, slot i / worldSize).  Host arithmetic only (an
+ * exclusive prefix sum over numChunks x 3 integers): counts / offsets are [numChunks][3] in linear
+ * chunk order, totals[3] the sizes of the assembled arrays. */
+int lvn_global_mesh_offsets(const int32_t *gathered, int worldSize, int perRank, int numChunks,
+                            int64_t *counts, int64_t *offsets, int64_t totals[3]);
 
 /* ---- utilities of the path (a9, a15), usable on their own ---------------- */
 

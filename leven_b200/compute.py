@@ -31,7 +31,7 @@ MAX_MESH_VERTICES = 14 * 1024          # render_types.h:62-68 (LEVEN defined)
 MAX_MESH_TRIANGLES = MAX_MESH_VERTICES * 2
 RenderShape_Cube, RenderShape_Sphere = 0, 1   # render_types.h:11-20
 
-LVN_STAGES = ("columns", "classify", "hermite", "leaves", "field", "csg", "cuckoo")
+LVN_STAGES = ("columns", "classify", "hermite", "leaves", "field", "csg", "cuckoo", "solve")
 
 # POD layouts (static_asserted against the C header in tests/test_abi.py)
 MeshVertex = np.dtype([("xyz", np.float32, 4), ("normal", np.float32, 4), ("colour", np.float32, 4)])
@@ -120,6 +120,7 @@ ABI = {
     "lvn_alloc_pinned": (_P, [C.c_size_t]),
     "lvn_free_pinned": (None, [_P]),
     "lvn_measure_fp32_peak": (_I, [_P]),
+    "lvn_global_mesh_offsets": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "lvn_find_next_prime": (_I, [_I]),
     "lvn_exclusive_scan": (_I, [_P, _P, _I]),
     "lvn_compact_index_array": (_I, [_P, _P, _I, _P]),
@@ -147,11 +148,15 @@ def lib():
     """Load libleven_b200.so; fails loudly when the CUDA extension has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = LIB_PATH
+        variant = os.environ.get("LVN_LIB_VARIANT")     # experiment builds: profiles/build_variant.sh <name> <nvcc flags>
+        if variant:
+            path = LIB_PATH[:-3] + "." + variant + ".so"
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                 "leven_b200 has no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in ABI.items():
             fn = getattr(L, name)
             fn.restype = res
@@ -459,6 +464,12 @@ def MeasureFP32Peak():
 
 
 # ---- utilities of the path (compute.cpp:328-543, compute_cuckoo.h) -------------
+def GlobalMeshOffsets(gathered, world_size, per_rank, num_chunks, counts, offsets, totals):
+    """lvn_global_mesh_offsets into caller-owned int64 arrays counts[n, 3], offsets[n, 3], totals[3]"""
+    return lib().lvn_global_mesh_offsets(_ptr(gathered), int(world_size), int(per_rank), int(num_chunks),
+                                         _ptr(counts), _ptr(offsets), _ptr(totals))
+
+
 def FindNextPrime(n):
     return lib().lvn_find_next_prime(int(n))
 

@@ -118,6 +118,7 @@ struct Global {
     bool deviceChosen = false;
     std::vector<uint8_t> image;
     float2 *d_grad2 = nullptr;
+    float *d_grad2x = nullptr;     // x plane, then y plane
     float4 *d_grad3 = nullptr;
     int defaultMaterial = 0;
     int densityKind = 0;
@@ -132,6 +133,7 @@ static DensityParams density_params()
 {
     DensityParams dp;
     dp.grad2 = g.d_grad2;
+    dp.grad2x = g.d_grad2x;
     dp.grad3 = g.d_grad3;
     dp.kind = g.densityKind;
     dp.param = g.densityParam;
@@ -282,6 +284,10 @@ static int upload_noise_image()
     }
     if (!g.d_grad2) CU(cudaMalloc((void **)&g.d_grad2, g2.size() * sizeof(float2)));
     if (!g.d_grad3) CU(cudaMalloc((void **)&g.d_grad3, 65536 * sizeof(float4)));
+    std::vector<float> planes(2 * g2.size());
+    for (size_t i = 0; i < g2.size(); i++) { planes[i] = g2[i].x; planes[g2.size() + i] = g2[i].y; }
+    if (!g.d_grad2x) CU(cudaMalloc((void **)&g.d_grad2x, planes.size() * sizeof(float)));
+    CU(cudaMemcpy(g.d_grad2x, planes.data(), planes.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_grad2, g2.data(), g2.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_grad3, g3.data(), 65536 * sizeof(float4), cudaMemcpyHostToDevice));
     return LVN_SUCCESS;
@@ -337,6 +343,8 @@ extern "C" int lvn_compute_shutdown(void)
 {
     if (g.d_grad2) cudaFree(g.d_grad2);
     if (g.d_grad3) cudaFree(g.d_grad3);
+    if (g.d_grad2x) cudaFree(g.d_grad2x);
+    g.d_grad2x = nullptr;
     g.d_grad2 = nullptr;
     g.d_grad3 = nullptr;
     g.initialised = false;
@@ -453,6 +461,7 @@ struct lvn_meshgen {
     DevBuf<float4> d_edgeInfo;
     DevBuf<int2> d_xzList;         // (chunk, edge slot) of every x/z edge of a lane: the Hermite search list
     DevBuf<lvn_mesh_vertex> d_vertices;
+    DevBuf<float4> d_qef;          // 4 x float4 per slot of the vertex arena: the QEF records between k_leaves and k_solve
     DevBuf<int> d_tris;
     DevBuf<lvn_seam_node_info> d_seams;
     DevBuf<uint4> d_slab;
@@ -568,7 +577,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_descs.release(); ctx->d_hdrs.release(); ctx->d_heights.release();
     ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
     ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release(); ctx->d_xzList.release();
-    ctx->d_vertices.release(); ctx->d_tris.release(); ctx->d_seams.release();
+    ctx->d_vertices.release(); ctx->d_qef.release(); ctx->d_tris.release(); ctx->d_seams.release();
     ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release();
     ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
     ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
@@ -897,6 +906,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
     LV(ctx->d_xzList.reserve(ctx->d_edgeKeys.cap));
     LV(ctx->d_vertices.reserve(std::max<size_t>((size_t)n * 2048, 1u << 16)));
+    LV(ctx->d_qef.reserve(ctx->d_vertices.cap * 4));
     LV(ctx->d_tris.reserve(ctx->d_vertices.cap * 6 * 2));
     LV(ctx->d_seams.reserve(std::max<size_t>((size_t)n * 512, 1u << 14)));
 
@@ -906,6 +916,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         int *hMin = (int *)(hb + (size_t)numColSets * sizeof(int4)), *hMax = hMin + numColSets;
         for (int k = 0; k < numColSets; k++) { hMin[k] = 0x7f7f7f7f; hMax[k] = (int)0x80808080u; }   // ordered keys of +3.4e38 / -3.4e38
     }
+    const double hostPrepDone = ctx->trace ? host_now_us() : 0.0;
     {   // one upload instead of two and two memsets (measured against a kernel that reads the mapped staging
         // block itself, profiles/r01s_notes.md: the copy is as fast or faster)
         const size_t headBytes = headColOffset + (size_t)numColSets * (sizeof(int4) + 2 * sizeof(int));
@@ -1017,14 +1028,20 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             }
             LVN_TRACE_EV(2);
             {
-                StageTimer t(ctx, LVN_STAGE_LEAVES, 1);
                 NodeDebug dbg = {};
                 if (opts.debug) {
                     dbg.codes = ctx->d_dbgCodes.p; dbg.edgeMasks = ctx->d_dbgMasks.p; dbg.matWords = ctx->d_dbgMats.p;
                     dbg.qefs = ctx->d_dbgQefs.p; dbg.positions = ctx->d_dbgPos.p; dbg.normals = ctx->d_dbgNrm.p;
                 }
-                launch_leaves(dp, d, ctx->d_descs.p, hdrs, ws, lane, nullptr,
-                              ctx->d_edgeInfo.p, ctx->d_vertices.p, ctx->d_tris.p, ctx->d_seams.p, dbg, ls);
+                {
+                    StageTimer t(ctx, LVN_STAGE_LEAVES, 1);
+                    launch_leaves(dp, d, ctx->d_descs.p, hdrs, ws, lane, nullptr, ctx->d_edgeInfo.p, ctx->d_qef.p,
+                                  ctx->d_vertices.p, ctx->d_tris.p, ctx->d_seams.p, dbg, ls);
+                }
+                {
+                    StageTimer t(ctx, LVN_STAGE_SOLVE, 1);
+                    launch_solve(ctx->d_descs.p, lane, ctx->d_qef.p, ctx->d_vertices.p, ctx->d_seams.p, dbg.positions, ls);
+                }
             }
             LVN_TRACE_EV(3);
             if (earlyPublish) CU(cudaEventRecord(ctx->evLane[k], ls));
@@ -1091,8 +1108,9 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         LV(join_lanes(ctx, R, out != nullptr && S > 1));
         if (ctx->trace) {
             hostWaited += host_now_us() - j0;
-            fprintf(stderr, "[lvn trace] host thread: %.0f us in the call, %.0f us of them waiting for the GPU (the rest: building the batch, driver calls)\n",
-                    host_now_us() - hostStart, hostWaited);
+            fprintf(stderr, "[lvn trace] host thread: %.0f us in the call, %.0f us of them waiting for the GPU (the rest: building the batch, driver calls); "
+                            "%.0f us before the first enqueue, everything enqueued after %.0f us\n",
+                    host_now_us() - hostStart, hostWaited, hostPrepDone - hostStart, j0 - hostStart);
         }
         CU(cudaGetLastError());
         collect_stage_times(ctx);
@@ -1139,6 +1157,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         LV(ctx->d_edgeInfo.reserve(ctx->d_edgeKeys.cap));
         LV(ctx->d_xzList.reserve(ctx->d_edgeKeys.cap));
         LV(ctx->d_vertices.reserve((size_t)S * ((size_t)mx.nodes + mx.nodes / 8 + 1024)));
+        LV(ctx->d_qef.reserve(ctx->d_vertices.cap * 4));
         LV(ctx->d_tris.reserve((size_t)S * ((size_t)mx.quads + mx.quads / 8 + 1024) * 6));
         LV(ctx->d_seams.reserve((size_t)S * ((size_t)mx.seams + mx.seams / 8 + 1024)));
     }
@@ -1836,6 +1855,25 @@ extern "C" int lvn_meshgen_debug_dump_chunk(lvn_meshgen *ctx, const int32_t min[
 // ---------------------------------------------------------------------------
 // utilities (a9, a15)
 // ---------------------------------------------------------------------------
+extern "C" int lvn_global_mesh_offsets(const int32_t *gathered, int worldSize, int perRank, int numChunks,
+                                       int64_t *counts, int64_t *offsets, int64_t totals[3])
+{
+    if (!gathered || !counts || !offsets || !totals || worldSize < 1 || perRank < 0 || numChunks < 0 ||
+        (int64_t)numChunks > (int64_t)worldSize * perRank) return LVN_ERR_INVALID_VALUE;
+    int64_t run[3] = {0, 0, 0};
+    for (int i = 0; i < numChunks; i++) {
+        const int32_t *src = gathered + ((size_t)(i % worldSize) * 3) * (size_t)perRank + (size_t)(i / worldSize);
+        for (int k = 0; k < 3; k++) {
+            const int64_t c = src[(size_t)k * perRank];
+            counts[3 * (size_t)i + k] = c;
+            offsets[3 * (size_t)i + k] = run[k];
+            run[k] += c;
+        }
+    }
+    totals[0] = run[0]; totals[1] = run[1]; totals[2] = run[2];
+    return LVN_SUCCESS;
+}
+
 extern "C" int lvn_find_next_prime(int n) { return host_find_next_prime(n); }
 
 extern "C" int lvn_exclusive_scan(const int32_t *data, int32_t *scan, int count)

@@ -195,16 +195,39 @@ __device__ __forceinline__ float2 rep2(float v) { return make_float2(v, v); }
 // packed product, uncontractable (see above)
 __device__ __forceinline__ float2 mul2(float2 a, float2 b, float2 nz) { return __ffma2_rn(a, b, nz); }
 
-__device__ __forceinline__ float2 corner2x2(const float2 gA, const float2 gB, float2 x, float2 y, float2 nz)
+// Gradient operands of a packed corner: (.x of position A, .x of position B) and the same for .y,
+// so that the corner's dot product is two packed instructions.  With the gradient fetched as one
+// float2 per position (LVN_X2_SPLIT_GRAD=0) the dot product has to stay scalar -- four scalar FP
+// instructions per corner between packed ones, and every switch between packed and scalar FP costs
+// the FMA pipe about a cycle (profiles/micro/ffma2_rate.cu).  The split tables (two float arrays, same
+// 257-pitch layout) deliver the components directly as register pairs.
+#ifndef LVN_X2_SPLIT_GRAD
+#define LVN_X2_SPLIT_GRAD 0   // measured (B200, ring): 0 = 185.2 us, 1 = 191.4 us (twice the gathers), 2 = float2 loads + MOV transposes
+#endif
+struct GradTables {
+    const float2 *g;     // [257*257] (x, y) per texel
+    const float *gx;     // [257*257]
+    const float *gy;     // [257*257]
+};
+__device__ __forceinline__ GradTables grad_tables(const DensityParams &dp)
+{
+    GradTables t; t.g = dp.grad2; t.gx = dp.grad2x; t.gy = dp.grad2x + LVN_G2PITCH * LVN_G2PITCH; return t;
+}
+
+__device__ __forceinline__ float2 corner2x2(const float2 gx, const float2 gy, float2 x, float2 y, float2 nz)
 {
     const float2 t0 = sub2(rep2(0.5f), fma2(y, y, mul2(x, x, nz)));
-    const float2 d = make_float2(__fmaf_rn(gA.y, y.x, gA.x * x.x), __fmaf_rn(gB.y, y.y, gB.x * x.y));
+#if LVN_X2_SPLIT_GRAD
+    const float2 d = fma2(gy, y, mul2(gx, x, nz));      // fma(g.y, y, g.x * x) per position, as in corner2()
+#else
+    const float2 d = make_float2(__fmaf_rn(gy.x, y.x, gx.x * x.x), __fmaf_rn(gy.y, y.y, gx.y * x.y));
+#endif
     const float2 tc = make_float2(fmaxf(t0.x, 0.f), fmaxf(t0.y, 0.f));
     const float2 t = mul2(tc, tc, nz);
     return mul2(mul2(t, t, nz), d, nz);
 }
 
-__device__ __forceinline__ float2 snoise2x2(const float2 *__restrict__ grad, float2 px, float2 py, float2 nz)
+__device__ __forceinline__ float2 snoise2x2(const GradTables grad, float2 px, float2 py, float2 nz)
 {
 #ifndef LVN_X2_XU_FLOOR
     const float2 M = rep2(12582912.f);   // 1.5 * 2^23
@@ -227,14 +250,24 @@ __device__ __forceinline__ float2 snoise2x2(const float2 *__restrict__ grad, flo
 #else
     const float2 o1y = make_float2(xyA ? 0.f : 1.f, xyB ? 0.f : 1.f);
 #endif
-    const float2 *gA = grad + ((jjA & 255) * LVN_G2PITCH + (iiA & 255));
-    const float2 *gB = grad + ((jjB & 255) * LVN_G2PITCH + (iiB & 255));
-    const float2 g0A = __ldg(gA), g1A = __ldg(gA + (xyA ? 1 : LVN_G2PITCH)), g2A = __ldg(gA + (LVN_G2PITCH + 1));
-    const float2 g0B = __ldg(gB), g1B = __ldg(gB + (xyB ? 1 : LVN_G2PITCH)), g2B = __ldg(gB + (LVN_G2PITCH + 1));
+    const int oA = (jjA & 255) * LVN_G2PITCH + (iiA & 255), oB = (jjB & 255) * LVN_G2PITCH + (iiB & 255);
+    const int o1A = oA + (xyA ? 1 : LVN_G2PITCH), o1B = oB + (xyB ? 1 : LVN_G2PITCH);
+#if LVN_X2_SPLIT_GRAD == 1
+    const float2 g0x = make_float2(__ldg(grad.gx + oA), __ldg(grad.gx + oB)), g0y = make_float2(__ldg(grad.gy + oA), __ldg(grad.gy + oB));
+    const float2 g1x = make_float2(__ldg(grad.gx + o1A), __ldg(grad.gx + o1B)), g1y = make_float2(__ldg(grad.gy + o1A), __ldg(grad.gy + o1B));
+    const float2 g2x = make_float2(__ldg(grad.gx + oA + (LVN_G2PITCH + 1)), __ldg(grad.gx + oB + (LVN_G2PITCH + 1)));
+    const float2 g2y = make_float2(__ldg(grad.gy + oA + (LVN_G2PITCH + 1)), __ldg(grad.gy + oB + (LVN_G2PITCH + 1)));
+#else
+    const float2 g0A = __ldg(grad.g + oA), g1A = __ldg(grad.g + o1A), g2A = __ldg(grad.g + oA + (LVN_G2PITCH + 1));
+    const float2 g0B = __ldg(grad.g + oB), g1B = __ldg(grad.g + o1B), g2B = __ldg(grad.g + oB + (LVN_G2PITCH + 1));
+    const float2 g0x = make_float2(g0A.x, g0B.x), g0y = make_float2(g0A.y, g0B.y);
+    const float2 g1x = make_float2(g1A.x, g1B.x), g1y = make_float2(g1A.y, g1B.y);
+    const float2 g2x = make_float2(g2A.x, g2B.x), g2y = make_float2(g2A.y, g2B.y);
+#endif
 
-    const float2 n0 = corner2x2(g0A, g0B, x0, y0, nz);
-    const float2 n1 = corner2x2(g1A, g1B, add2(sub2(x0, o1x), rep2(LVN_G2)), add2(sub2(y0, o1y), rep2(LVN_G2)), nz);
-    const float2 n2 = corner2x2(g2A, g2B, sub2(x0, rep2(1.f - 2.f * LVN_G2)), sub2(y0, rep2(1.f - 2.f * LVN_G2)), nz);
+    const float2 n0 = corner2x2(g0x, g0y, x0, y0, nz);
+    const float2 n1 = corner2x2(g1x, g1y, add2(sub2(x0, o1x), rep2(LVN_G2)), add2(sub2(y0, o1y), rep2(LVN_G2)), nz);
+    const float2 n2 = corner2x2(g2x, g2y, sub2(x0, rep2(1.f - 2.f * LVN_G2)), sub2(y0, rep2(1.f - 2.f * LVN_G2)), nz);
     return mul2(rep2(70.f), add2(add2(n0, n1), n2), nz);
 }
 
@@ -272,7 +305,7 @@ static __constant__ OctaveTable<2> c_x2_b2Amp = amplitude_table<2>(0.15f);
 #endif
 
 template <int OCTAVES>
-__device__ __forceinline__ float2 basic_fractal_x2(const float2 *__restrict__ grad, float frequency, float lacunarity,
+__device__ __forceinline__ float2 basic_fractal_x2(const GradTables grad, float frequency, float lacunarity,
                                                    float persistence, const float *amp, float2 px, float2 py, float2 nz)
 {
     float2 noise = rep2(0.f);
@@ -299,7 +332,7 @@ __device__ __forceinline__ float2 basic_fractal_x2(const float2 *__restrict__ gr
 }
 
 template <int OCTAVES>
-__device__ __forceinline__ float2 ridged_multifractal_x2(const float2 *__restrict__ grad, float lacunarity, float gain,
+__device__ __forceinline__ float2 ridged_multifractal_x2(const GradTables grad, float lacunarity, float gain,
                                                          float offset, const float *expo, float2 px, float2 py, float2 nz)
 {
     float2 signal = snoise2x2(grad, px, py, nz);
@@ -332,9 +365,9 @@ __device__ __forceinline__ float2 ridged_multifractal_x2(const float2 *__restric
 
 // terrain_height() at (xA, zA) and (xB, zB): x = (xA, xB), z = (zA, zB); negZero must be -0.f
 #ifdef LVN_X2_NOINLINE
-__device__ __noinline__ float2 terrain_height_x2(const float2 *__restrict__ grad, float negZero, float2 x, float2 z)
+__device__ __noinline__ float2 terrain_height_x2(const GradTables grad, float negZero, float2 x, float2 z)
 #else
-__device__ __forceinline__ float2 terrain_height_x2(const float2 *__restrict__ grad, float negZero, float2 x, float2 z)
+__device__ __forceinline__ float2 terrain_height_x2(const GradTables grad, float negZero, float2 x, float2 z)
 #endif
 {
     const float2 nz = rep2(negZero);

@@ -92,6 +92,7 @@ struct ChunkScratch {
 
 struct DensityParams {
     const float2 *grad2;      // [257*257] snoise2 gradients (texel.xy * 4 - 1), wrap-padded
+    const float *grad2x;      // [2][257*257] the same table as separate x and y planes (density.cuh: GradTables)
     const float4 *grad3;      // [256*256] snoise3 gradients xyz, w = bits of the perm column
     int kind;                 // 0 terrain, 1 stress
     float param;              // stress threshold
@@ -130,8 +131,11 @@ void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *des
                     int2 *xzList, cudaStream_t s);
 void launch_leaves(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
                    ChunkScratch ws, LaneArenas lane, ArenaCounters *hostCounters, const float4 *edgeInfo,
+                   void *qefScratch,   // 64 B per slot of the vertex arena: k_leaves -> k_solve
                    lvn_mesh_vertex *vertices, int *triIndices, lvn_seam_node_info *seams,
                    NodeDebug dbg, cudaStream_t s);
+void launch_solve(const ChunkDesc *descs, LaneArenas lane, const void *qefScratch, lvn_mesh_vertex *vertices,
+                  lvn_seam_node_info *seams, float4 *dbgPositions, cudaStream_t s);
 
 // ---- launchers (kernels_csg.cu) -------------------------------------------
 struct CsgOpDev {          // CSGOperation + host-computed cos/sin of rotateY
