@@ -466,6 +466,7 @@ struct lvn_meshgen {
     DevBuf<lvn_seam_node_info> d_seams;
     DevBuf<uint4> d_slab;
     DevBuf<unsigned int> d_slabEy, d_ticket;
+    DevBuf<int> d_candidates;      // per lane slice: the chunks that can contain surface (k_candidates -> k_rows)
     DevBuf<TileRef> d_edgeTiles, d_nodeTiles;  // tile directories, one slice per lane
     DevBuf<uint8_t> d_tmpFields;
     DevBuf<uint8_t *> d_fieldPtrs;
@@ -578,7 +579,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_bitsLo.release(); ctx->d_bitsHi.release(); ctx->d_rowE.release(); ctx->d_rowN.release();
     ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release(); ctx->d_xzList.release();
     ctx->d_vertices.release(); ctx->d_qef.release(); ctx->d_tris.release(); ctx->d_seams.release();
-    ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release();
+    ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release(); ctx->d_candidates.release();
     ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
     ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
@@ -890,8 +891,9 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     LV(ctx->d_rowN.reserve(n * VV));
     LV(ctx->d_rowQ.reserve(n * VV));
     LV(ctx->d_rowS.reserve(n * VV));
-    LV(ctx->d_slab.reserve((size_t)n * LVN_MAX_SLABS));
-    LV(ctx->d_slabEy.reserve((size_t)n * LVN_MAX_SLABS));
+    LV(ctx->d_slab.reserve((size_t)n * LVN_MAX_LAYERS));
+    LV(ctx->d_slabEy.reserve((size_t)n * LVN_MAX_LAYERS));
+    LV(ctx->d_candidates.reserve(n));
     if ((size_t)n > ctx->d_ticket.cap) {
         LV(ctx->d_ticket.reserve(n));
         CU(cudaMemsetAsync(ctx->d_ticket.p, 0, ctx->d_ticket.cap * sizeof(unsigned int), st));   // k_rows leaves it zero
@@ -929,7 +931,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
     ChunkScratch ws;
     ws.bitsLo = ctx->d_bitsLo.p; ws.bitsHi = ctx->d_bitsHi.p;
     ws.rowE = ctx->d_rowE.p; ws.rowN = ctx->d_rowN.p; ws.rowQ = ctx->d_rowQ.p; ws.rowS = ctx->d_rowS.p;
-    ws.slab = ctx->d_slab.p; ws.slabEy = ctx->d_slabEy.p; ws.ticket = ctx->d_ticket.p;
+    ws.layer = ctx->d_slab.p; ws.layerEy = ctx->d_slabEy.p; ws.ticket = ctx->d_ticket.p;
 
     // ---- S1 for the whole batch: the column sets are shared between the lanes ----
     if (numColSets) {
@@ -1004,9 +1006,9 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             lane.tileCap = tileCap;
             ctx->laneBase[k] = lane.base;
             {
-                StageTimer t(ctx, LVN_STAGE_CLASSIFY, 1);
+                StageTimer t(ctx, LVN_STAGE_CLASSIFY, 2);
                 launch_rows(d, ctx->d_descs.p, first, cnt, ctx->d_heights.p, d_colMin, d_colMax, hdrs, nullptr,
-                            ws, lane, ls);
+                            ws, lane, ctx->d_candidates.p, ls);
             }
             // The lane's headers and counters are final once k_rows has run.  On the host path they
             // are published right away from a side stream, so that the host can size and queue the

@@ -47,6 +47,7 @@ struct ArenaCounters {
     unsigned int nonEmpty;
     unsigned int edgeTiles, nodeTiles;   // entries of the tile directories
     unsigned int xzEdges;                // entries of the lane's x/z-edge search list (k_hermite_locate)
+    unsigned int candidates;             // chunks of the lane that can contain surface (k_candidates): k_rows' list
 };
 
 // Tile directories: the Hermite and leaf kernels run one block per tile of LVN_TILE consecutive
@@ -72,22 +73,21 @@ struct Dims {
     int depth;          // MAX_OCTREE_DEPTH
 };
 
-// A chunk is cut into slabs of LVN_SLAB_Z z layers (one k_rows block each); row offsets are
-// relative to the slab, the slab records hold the slab's exclusive base.
-constexpr int LVN_SLAB_Z = 6;
-constexpr int LVN_MAX_SLABS = 11;   // ceil(66 / 6)
+// k_rows works per z layer (one warp each); row offsets are relative to the layer, the layer
+// records hold the layer's exclusive base.
+constexpr int LVN_MAX_LAYERS = 66;   // F for V = 64
 
 // Per-chunk scratch that links k_rows to the Hermite and leaf kernels.
 struct ChunkScratch {
     unsigned long long *bitsLo;   // [n][F*F] solid bits x 0..63 of row (z*F + y)
     unsigned int *bitsHi;         // [n][F*F] solid bits x 64..
-    unsigned int *rowE;           // [n][H*H] slab-relative exclusive edge offsets per Hermite row (z*H + y)
-    unsigned int *rowN;           // [n][V*V] slab-relative exclusive node offsets per voxel row (z*V + y)
+    unsigned int *rowE;           // [n][H*H] layer-relative exclusive edge offsets per Hermite row (z*H + y)
+    unsigned int *rowN;           // [n][V*V] layer-relative exclusive node offsets per voxel row (z*V + y)
     unsigned int *rowQ;           // [n][V*V] quads
     unsigned int *rowS;           // [n][V*V] seam nodes
-    uint4 *slab;                  // [n][LVN_MAX_SLABS] exclusive (edge, node, quad, seam) base of each slab
-    unsigned int *slabEy;         // [n][LVN_MAX_SLABS] y edges of each slab (stage accounting)
-    unsigned int *ticket;         // [n] slabs finished; zero between batches
+    uint4 *layer;                 // [n][LVN_MAX_LAYERS] exclusive (edge, node, quad, seam) base of each z layer
+    unsigned int *layerEy;        // [n][LVN_MAX_LAYERS] y edges of each layer (stage accounting)
+    unsigned int *ticket;         // [n] layers finished; zero between batches
 };
 
 struct DensityParams {
@@ -123,7 +123,7 @@ void launch_field_density(const DensityParams &dp, const Dims &d, const ChunkDes
 // hostHdrs / hostCounters: mapped pinned mirrors written directly by the kernels
 void launch_rows(const Dims &d, const ChunkDesc *descs, int first, int n, const float *heights,
                  const int *colMin, const int *colMax, ChunkHdr *hdrs, ChunkHdr *hostHdrs, ChunkScratch ws,
-                 LaneArenas lane, cudaStream_t s);
+                 LaneArenas lane, int *candidateList /* [n chunks of the batch] */, cudaStream_t s);
 // hostHdrs / hostCounters may be null: launch_publish then mirrors the lane's header slots
 void launch_publish(const ChunkHdr *devHdrs, ChunkHdr *hostHdrs, int count, cudaStream_t s);
 void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
