@@ -26,8 +26,10 @@ struct vec4 { float x, y, z, w; };
 #define LVN_CL_ERROR (-99999)
 #endif
 
+#ifndef HAS_RENDER_TYPES_H_BEEN_INCLUDED
 // render_types.h:11-20
 enum RenderShape { RenderShape_Cube, RenderShape_Sphere, RenderShape_Line, RenderShape_SIZE, RenderShape_None };
+#endif
 
 // compute.h:16-24
 struct CSGOperationInfo {

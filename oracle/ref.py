@@ -52,8 +52,11 @@ def build(force=False):
     """compile the reference kernels where they lie; a no-op (returns False) when /root/reference is absent"""
     if not os.path.isdir(REFERENCE_CL):
         return available()
-    deps = [os.path.join(_HERE, "ref_shim", f) for f in ("ref_kernels.cpp", "clc.hpp", "translate.py")] + [os.path.join(_HERE, "Makefile")]
+    deps = [os.path.join(_HERE, "ref_shim", f) for f in ("ref_kernels.cpp", "clc.hpp", "translate.py", "ref_clipmap_caller.cpp")] + \
+           [os.path.join(_HERE, "Makefile"), os.path.join(os.path.dirname(_HERE), "include", "leven_compute.hpp")]
     libs = [_lib_path(V) for V in (64, 32, 16)]
+    if os.path.exists(PRODUCT_LIB_PATH):
+        libs.append(CALLER_LIB_PATH)      # links against the product library: built once that exists
     stale = any(not os.path.exists(l) for l in libs) or any(os.path.getmtime(d) > min(os.path.getmtime(l) for l in libs) for d in deps)
     if force or stale:
         env = dict(os.environ)
@@ -467,6 +470,40 @@ SIMPLIFY_DEFAULTS = dict(edgeFraction=0.125, maxIterations=10, targetPercentage=
 
 def simplify_available():
     return os.path.exists(SIMPLIFY_LIB_PATH)
+
+
+# ---- the reference's own caller (clipmap.cpp:329-504) on top of the C ABI: ref_shim/ref_clipmap_caller.cpp ----
+PRODUCT_LIB_PATH = os.path.join(os.path.dirname(_HERE), "leven_b200", "lib", "libleven_b200.so")
+CALLER_LIB_PATH = os.path.join(_HERE, "_ref", "libleven_clipmap_caller.so")
+_caller_lib = None
+
+
+def caller_available():
+    return os.path.exists(CALLER_LIB_PATH)
+
+
+def caller_construct_node(mn, size, collision=False, voxels_per_chunk=64, mesh_max_error=5.0, mesh_max_edge_len=2.5,
+                          mesh_max_angle=0.7):
+    """ConstructClipmapNodeData / ConstructCollisionNodeData (clipmap.cpp:431-504) -- the reference's own code,
+    compiled against include/leven_compute.hpp -- for one node.  The process must have initialised the product
+    library (Compute_Initialise).  Returns dict(vertices, triangles, seamMinSize, seamPosition, seamNormal,
+    seamColour, seamMaterial, active)."""
+    global _caller_lib
+    if _caller_lib is None:
+        _caller_lib = C.CDLL(CALLER_LIB_PATH)
+    v = np.zeros(14 * 1024, VERTEX_DTYPE); t = np.zeros((28 * 1024, 3), np.int32)
+    cap = 64 * 64 * 6 + 16
+    sm = np.zeros((cap, 4), np.int32); sf = np.zeros((cap, 9), np.float32); mat = np.zeros(cap, np.int32)
+    nv, nt, ns, act = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    f = C.c_float
+    m3 = np.array(list(mn)[:3], np.int32)
+    rc = _caller_lib.refcaller_construct_node(int(voxels_per_chunk), int(bool(collision)), _p(m3), int(size), f(mesh_max_error),
+                                              f(mesh_max_edge_len), f(mesh_max_angle), _p(v), len(v), C.byref(nv), _p(t), len(t),
+                                              C.byref(nt), _p(sm), _p(sf), _p(mat), cap, C.byref(ns), C.byref(act))
+    assert rc == 0, rc
+    n = ns.value
+    return dict(vertices=v[:nv.value].copy(), triangles=t[:nt.value].copy(), seamMinSize=sm[:n].copy(), seamPosition=sf[:n, 0:3].copy(),
+                seamNormal=sf[:n, 3:6].copy(), seamColour=sf[:n, 6:9].copy(), seamMaterial=mat[:n].copy(), active=bool(act.value))
 
 
 def simplify_lib():

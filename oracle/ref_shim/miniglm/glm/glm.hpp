@@ -4,6 +4,7 @@
 // Only integer / float vectors with component-wise arithmetic: nothing here decides a result
 // beyond IEEE / two's-complement arithmetic on the components.
 #pragma once
+#define GLM_VERSION 93   // GLM 0.9.3.x defines it (core/setup.hpp); include/leven_compute.hpp keys its glm support on it
 #include <cfloat>
 #include <cmath>
 #include <cstddef>

@@ -11,6 +11,9 @@ For the reference's C++ (leven/src/octree.cpp, the seam octree) nothing is rewri
 --drop-include removes #include lines of headers whose own includes cannot be satisfied here
 (window system, renderer, thread pool: render.h, volume.h, ...) -- the two functions and one
 constant octree.cpp takes from them are supplied by oracle/ref_shim/ref_octree.cpp.
+--lines A-B keeps only that (1-based, inclusive) slice of a file, verbatim, behind a #line directive:
+clipmap.cpp's mesh-data functions (GenerateMeshDataForNode .. ConstructCollisionNodeData) are compiled
+that way against include/leven_compute.hpp, without the renderer / physics / thread code around them.
 The output is a build intermediate under oracle/_ref/ (git-ignored, deleted after the build).
 """
 import os
@@ -18,7 +21,14 @@ import re
 import sys
 
 
-def translate(text, src_path, drop=()):
+def translate(text, src_path, drop=(), ranges=()):
+    if ranges:
+        lines = text.split("\n")
+        parts = []
+        for a, b in ranges:
+            parts.append('#line %d "%s"' % (a, src_path))
+            parts.extend(lines[a - 1:b])
+        return "\n".join(parts) + "\n"
     for h in drop:
         text = re.sub(r'^[ \t]*#include\s+"%s".*$' % re.escape(h), "// (include of %s dropped)" % h, text, flags=re.M)
     if src_path.endswith((".cpp", ".h")):
@@ -34,7 +44,9 @@ def translate(text, src_path, drop=()):
 if __name__ == "__main__":
     src, dst = sys.argv[1], sys.argv[2]
     drop = [sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == "--drop-include"]
+    # --lines A-B (repeatable): only that slice of a C++ source, verbatim (clipmap.cpp's mesh-data functions)
+    ranges = [tuple(int(v) for v in sys.argv[i + 1].split("-")) for i, a in enumerate(sys.argv) if a == "--lines"]
     with open(src, encoding="utf-8", errors="replace") as f:
-        out = translate(f.read(), os.path.abspath(src), drop)
+        out = translate(f.read(), os.path.abspath(src), drop, ranges)
     with open(dst, "w") as f:
         f.write(out)

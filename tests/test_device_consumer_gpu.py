@@ -1,0 +1,71 @@
+"""The no-readback path (second half; VERDICT r01 missing item 2): the reference's stated
+main problem is that every mesh is downloaded and re-uploaded for rendering (README.md:32-36).
+lvn_meshgen_generate_batch_device leaves the exported arenas in HBM and hands out device pointers; a
+graphics-API interop consumer would map its vertex / index buffers (cudaGraphicsResourceGetMappedPointer)
+and copy device-to-device.  There is no GL / Vulkan in this image, so the stand-in consumer is another
+CUDA library in the same process -- torch -- that wraps the arenas IN PLACE through
+__cuda_array_interface__ (no copy through the host), packs every chunk's slices into its own "vertex
+buffer" / "index buffer" tensors with device-to-device copies, rebases the indices the way a renderer's
+draw call would (baseVertex), and only then is compared with what the host path delivers."""
+import numpy as np
+import pytest
+
+import leven_b200.workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+class DeviceArray:
+    """zero-copy view of a device allocation for any __cuda_array_interface__ consumer"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+def test_device_arenas_consumed_in_place(lc):
+    torch = pytest.importorskip("torch")
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        ms = W.ring_chunks()[192:320]                       # 128 chunks through the surface layers
+        rc, res, view = ctx.generateBatchDevice(ms)
+        assert rc == 0 and view.totalVertices > 0
+        nV, nT = int(res["numVertices"].sum()), int(res["numTriangles"].sum())
+        # the consumer's own buffers (a renderer's VBO / IBO), filled device-to-device, chunk after chunk
+        vbo = torch.empty((nV, 48), dtype=torch.uint8, device="cuda")
+        ibo = torch.empty((nT, 3), dtype=torch.int32, device="cuda")
+        extent_v = int((res["vertexOffset"] + res["numVertices"]).max())
+        extent_t = int((res["triangleOffset"] + res["numTriangles"]).max())
+        dv = torch.as_tensor(DeviceArray(view.vertices, extent_v * 48), device="cuda").view(-1, 48)
+        dt = torch.as_tensor(DeviceArray(view.triangles, extent_t * 12), device="cuda").view(torch.int32).view(-1, 3)
+        assert dv.data_ptr() == int(view.vertices)          # in place: no staging copy was made
+        v0 = t0 = 0
+        draws = []
+        for r in res:
+            n, m = int(r["numVertices"]), int(r["numTriangles"])
+            if m == 0:
+                continue
+            vbo[v0:v0 + n] = dv[r["vertexOffset"]:r["vertexOffset"] + n]
+            ibo[t0:t0 + m] = dt[r["triangleOffset"]:r["triangleOffset"] + m] + v0      # baseVertex
+            draws.append((v0, n, t0, m))
+            v0 += n; t0 += m
+        assert v0 == nV and t0 == nT
+        # something a renderer-side pass would compute from the buffers, still on the device
+        xyz = vbo.view(torch.float32).view(-1, 12)[:, :3]
+        lo, hi = xyz.min(0).values.cpu().numpy(), xyz.max(0).values.cpu().numpy()
+        assert int(ibo.max()) < nV and int(ibo.min()) >= 0
+        # now the host path, for comparison only
+        V = np.zeros(nV + 1, lc.MeshVertex); T = np.zeros(nT + 1, lc.MeshTriangle); S = np.zeros(int(view.totalSeamNodes) + 1, lc.SeamNodeInfo)
+        rc, hres = ctx.generateBatch(ms, V, T, S)
+        assert rc == 0
+        hv = np.concatenate([V[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]] for r in hres if r["numTriangles"] > 0])
+        assert vbo.cpu().numpy().tobytes() == hv.tobytes()
+        base, parts = 0, []
+        for r in hres:
+            if r["numTriangles"] > 0:
+                parts.append(T["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]] + base)
+                base += r["numVertices"]
+        assert np.array_equal(ibo.cpu().numpy(), np.concatenate(parts))
+        assert np.all(lo >= ms[:, :3].min(0) - 4) and np.all(hi <= (ms[:, :3] + 256).max(0) + 4)
+        assert len(draws) == int((res["numTriangles"] > 0).sum())
+    finally:
+        ctx.destroy()
