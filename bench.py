@@ -658,7 +658,8 @@ def bench_csg(lc, ctx, torch, stream, flush, fp32_peak, hbm_peak):
     batch call, store the op.  Timed end to end per op with CUDA events on the context's stream
     (every call is synchronous, so the event interval is the call)."""
     ring = W.ring_chunks()
-    Vh = np.zeros(2000000, lc.MeshVertex); Th = np.zeros(4000000, lc.MeshTriangle); Sh = np.zeros(400000, lc.SeamNodeInfo)
+    keep = [torch.empty(n * sz, dtype=torch.uint8, pin_memory=True) for n, sz in ((400000, 48), (800000, 12), (100000, 48))]
+    Vh, Th, Sh = keep[0].numpy().view(lc.MeshVertex), keep[1].numpy().view(lc.MeshTriangle), keep[2].numpy().view(lc.SeamNodeInfo)
     ops = [lc.CSGOperationInfo.make(*s) for s in W.csg_script()]
     apply_ms, mesh_ms, wall_ms, edits = [], [], [], 0
     ctx.getStats(reset=True)

@@ -477,6 +477,13 @@ struct lvn_meshgen {
     DevBuf<float4> d_dbgPos, d_dbgNrm;
     // csg scratch
     DevBuf<unsigned int> d_touched, d_csgCounts;
+    // hash tables built without waiting for their insert flags (apply_csg_items): the flags land in
+    // h_tableFlags behind the stream's next synchronisation, run_batch looks at them before it trusts
+    // a result that read those tables (validate_pending_tables)
+    std::vector<FieldEntry *> pendingTables;
+    DevBuf<unsigned int> d_tableFlags;
+    PinBuf<unsigned int> h_tableFlags;
+    bool forceTableRetry = false;          // LVN_TEST_CUCKOO_RETRY=1: treat every first insertion as failed (tests)
     DevBuf<CsgOpDev> d_ops;
     DevBuf<CsgChunk> d_csgChunks;
     // simplified batch (lvn_meshgen_generate_simplified_batch)
@@ -565,6 +572,7 @@ extern "C" lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk)
     if (const char *e = getenv("LVN_LANES")) ctx->cfgLanes = atoi(e);
     if (const char *e = getenv("LVN_STREAMS")) ctx->cfgStreams = atoi(e);
     if (const char *e = getenv("LVN_TRACE")) ctx->trace = atoi(e) != 0;
+    if (const char *e = getenv("LVN_TEST_CUCKOO_RETRY")) ctx->forceTableRetry = atoi(e) != 0;
     return ctx;
 }
 
@@ -584,7 +592,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
-    ctx->d_ops.release(); ctx->d_csgChunks.release();
+    ctx->d_ops.release(); ctx->d_csgChunks.release(); ctx->d_tableFlags.release(); ctx->h_tableFlags.release();
     ctx->d_simpRes.release(); ctx->d_packOff.release(); ctx->d_packV.release(); ctx->d_packP.release(); ctx->d_packT.release();
     ctx->h_simpRes.release(); ctx->h_packOff.release();
     if (ctx->simpStreamB) cudaStreamDestroy(ctx->simpStreamB);
@@ -804,8 +812,20 @@ static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies)
 // One pass of the path over n chunks.  Results stay in the context's arenas; with `out` the
 // mesh / seam arenas of every lane are also copied into the caller's host arenas while the
 // following lanes are still computing.
+static int validate_pending_tables(lvn_meshgen *ctx, bool *rebuilt);
+constexpr int LVN_RETRY_TABLES = 1;   // internal: a hash table this batch read had to be rehashed, run the batch again
+
+static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const BatchOpts &opts, const HostOut *out);
+
 static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const BatchOpts &opts,
                      const HostOut *out = nullptr)
+{
+    int rc = run_batch_once(ctx, n, chunkMinSize, opts, out);
+    if (rc == LVN_RETRY_TABLES) rc = run_batch_once(ctx, n, chunkMinSize, opts, out);
+    return rc == LVN_RETRY_TABLES ? LVN_CL_ERROR : rc;
+}
+
+static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const BatchOpts &opts, const HostOut *out)
 {
     if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
     if (!ctx || n < 0 || (n > 0 && !chunkMinSize)) return LVN_ERR_INVALID_VALUE;
@@ -1014,7 +1034,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
             // are published right away from a side stream, so that the host can size and queue the
             // lane's copies (behind evLane) long before the lane's last kernel ends: the copy engine
             // then starts the moment the lane is done, with no host round trip in between.
-            const bool earlyPublish = out && S > 1;
+            const bool earlyPublish = out != nullptr;
             if (earlyPublish) {
                 CU(cudaEventRecord(ctx->evRows[k], ls));
                 CU(cudaStreamWaitEvent(ctx->pubStream, ctx->evRows[k], 0));
@@ -1023,7 +1043,9 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 ctx->stats.launches[LVN_STAGE_CLASSIFY] += 1;   // k_publish
             }
             LVN_TRACE_EV(1);
-            {
+            bool anyFresh = false;   // a lane of cached edge lists only (re-meshing edited chunks) has nothing for S3
+            for (int p = first; p < first + cnt && !anyFresh; p++) anyFresh = ctx->h_descs.p[p].edgeMode == EDGES_FRESH;
+            if (anyFresh) {
                 StageTimer t(ctx, LVN_STAGE_HERMITE, 1);
                 launch_hermite(dp, d, ctx->d_descs.p, hdrs, ws, lane, ctx->d_heights.p, ctx->d_edgeKeys.p,
                                ctx->d_edgeInfo.p, ctx->d_xzList.p, ls);
@@ -1067,8 +1089,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 while (issued < S && issued < k + 2) LV(enqueue_lane(issued++));
                 if (overflow || hostFull) continue;   // keep issuing: the retry needs every lane's counts
                 const double w0 = ctx->trace ? host_now_us() : 0.0;
-                if (S > 1) CU(cudaEventSynchronize(ctx->evPub[k]));
-                else CU(cudaStreamSynchronize(st));
+                CU(cudaEventSynchronize(ctx->evPub[k]));
                 if (ctx->trace) hostWaited += host_now_us() - w0;
                 const ArenaCounters c = *lane_counters_host(k);
                 if (c.overflow) { overflow = true; continue; }
@@ -1078,8 +1099,8 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
                 const ArenaCaps &b = ctx->laneBase[k];
                 // the lane's three arenas in one batched copy: 12 separate memcpys of a 4-lane batch
                 // cost ~55 us more than the same bytes in one (profiles/micro/copy_granularity.cu)
-                cudaStream_t cs = S > 1 ? ctx->copyStream : st;
-                if (S > 1) CU(cudaStreamWaitEvent(cs, ctx->evLane[k], 0));   // the lane's last kernel
+                cudaStream_t cs = ctx->copyStream;
+                CU(cudaStreamWaitEvent(cs, ctx->evLane[k], 0));   // the lane's last kernel
                 void *dst[3], *src[3];
                 size_t len[3];
                 size_t m = 0;
@@ -1107,7 +1128,7 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         }
 #undef LVN_TRACE_EV
         const double j0 = ctx->trace ? host_now_us() : 0.0;
-        LV(join_lanes(ctx, R, out != nullptr && S > 1));
+        LV(join_lanes(ctx, R, out != nullptr));
         if (ctx->trace) {
             hostWaited += host_now_us() - j0;
             fprintf(stderr, "[lvn trace] host thread: %.0f us in the call, %.0f us of them waiting for the GPU (the rest: building the batch, driver calls); "
@@ -1116,6 +1137,11 @@ static int run_batch(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, const
         }
         CU(cudaGetLastError());
         collect_stage_times(ctx);
+        {   // hash tables queued by the edit in front of this batch (apply_csg_items): their insert flags are in now
+            bool rebuilt = false;
+            LV(validate_pending_tables(ctx, &rebuilt));
+            if (rebuilt) return LVN_RETRY_TABLES;
+        }
         if (ctx->trace) {
             fprintf(stderr, "[lvn trace] n=%d lanes=%d streams=%d  (us since fork: start rows|hermite|leaves|d2h|end)\n", n, S, R);
             for (int k = 0; k < S; k++) {
@@ -1418,9 +1444,56 @@ static void draw_cuckoo_params(unsigned int *params8)
 // Cuckoo_InitialiseTable + Cuckoo_InsertKeys for every entry of the list: all fills and inserts
 // are queued, one host wait reads every failure flag, entries whose insertion failed are
 // rehashed with fresh parameters (the reference's loop, compute_cuckoo.cpp:89-132).
-static int build_cuckoo_tables(lvn_meshgen *ctx, const std::vector<FieldEntry *> &entries)
+static int validate_pending_tables(lvn_meshgen *ctx, bool *rebuilt);
+
+// queue Cuckoo_InitialiseTable + Cuckoo_InsertKeys with fresh parameters for every entry of the list; flag i
+// (device) becomes non-zero when a key of entry i could not be placed
+static int enqueue_table_builds(lvn_meshgen *ctx, const std::vector<FieldEntry *> &todo, unsigned int *d_flags, int attempt)
 {
     cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(d_flags, 0, todo.size() * sizeof(unsigned int), st));
+    for (size_t i = 0; i < todo.size(); i++) {
+        FieldEntry *fe = todo[i];
+        draw_cuckoo_params(fe->params);
+        launch_fill_u64(fe->d_table, fe->prime, ~0ull, st);
+        launch_cuckoo_insert((const unsigned int *)fe->d_keys, (unsigned int)fe->numEdges, fe->d_table, fe->prime, fe->params,
+                             d_flags + i, st);
+        fe->cuckooRetries = attempt;
+        ctx->stats.launches[LVN_STAGE_CUCKOO] += 2;
+    }
+    return LVN_SUCCESS;
+}
+
+// the reference's loop (compute_cuckoo.cpp:89-132): entries whose insertion failed are rehashed with fresh parameters
+static int retry_table_builds(lvn_meshgen *ctx, std::vector<FieldEntry *> todo, int firstAttempt)
+{
+    cudaStream_t st = ctx->stream;
+    LV(ctx->d_csgCounts.reserve(todo.size()));
+    LV(ctx->h_small.reserve(todo.size()));
+    for (int attempt = firstAttempt; attempt < 64 && !todo.empty(); attempt++) {
+        LV(enqueue_table_builds(ctx, todo, ctx->d_csgCounts.p, attempt));
+        CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, todo.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<FieldEntry *> failed;
+        for (size_t i = 0; i < todo.size(); i++)
+            if (ctx->h_small.p[i] != 0) failed.push_back(todo[i]);
+        todo.swap(failed);
+    }
+    return todo.empty() ? LVN_SUCCESS : LVN_CL_ERROR;
+}
+
+// Cuckoo_InitialiseTable + Cuckoo_InsertKeys for every entry of the list: all fills and inserts
+// are queued, one host wait reads every failure flag, entries whose insertion failed are
+// rehashed with fresh parameters.  defer: do not wait -- the first attempt almost always succeeds
+// (four hash functions at load 0.5); the flags are looked at behind the stream's next
+// synchronisation (validate_pending_tables), before any result that read the tables is trusted.
+static int build_cuckoo_tables(lvn_meshgen *ctx, const std::vector<FieldEntry *> &entries, bool defer = false)
+{
+    cudaStream_t st = ctx->stream;
+    if (!ctx->pendingTables.empty()) {      // an earlier deferred build nobody has looked at yet
+        CU(cudaStreamSynchronize(st));
+        LV(validate_pending_tables(ctx, nullptr));
+    }
     std::vector<FieldEntry *> todo;
     for (FieldEntry *fe : entries) {
         if (fe->d_table) { cudaFreeAsync(fe->d_table, st); fe->d_table = nullptr; }
@@ -1433,27 +1506,28 @@ static int build_cuckoo_tables(lvn_meshgen *ctx, const std::vector<FieldEntry *>
     }
     if (todo.empty()) return LVN_SUCCESS;
     StageTimer t(ctx, LVN_STAGE_CUCKOO, 0);
-    LV(ctx->d_csgCounts.reserve(todo.size()));
-    LV(ctx->h_small.reserve(todo.size()));
-    for (int attempt = 0; attempt < 64 && !todo.empty(); attempt++) {
-        CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, todo.size() * sizeof(unsigned int), st));
-        for (size_t i = 0; i < todo.size(); i++) {
-            FieldEntry *fe = todo[i];
-            draw_cuckoo_params(fe->params);
-            launch_fill_u64(fe->d_table, fe->prime, ~0ull, st);
-            launch_cuckoo_insert((const unsigned int *)fe->d_keys, (unsigned int)fe->numEdges, fe->d_table, fe->prime, fe->params,
-                                 ctx->d_csgCounts.p + i, st);
-            fe->cuckooRetries = attempt;
-            ctx->stats.launches[LVN_STAGE_CUCKOO] += 2;
-        }
-        CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, todo.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        std::vector<FieldEntry *> failed;
-        for (size_t i = 0; i < todo.size(); i++)
-            if (ctx->h_small.p[i] != 0) failed.push_back(todo[i]);
-        todo.swap(failed);
-    }
-    return todo.empty() ? LVN_SUCCESS : LVN_CL_ERROR;
+    if (!defer) return retry_table_builds(ctx, todo, 0);
+    LV(ctx->d_tableFlags.reserve(todo.size()));
+    LV(ctx->h_tableFlags.reserve(todo.size()));
+    LV(enqueue_table_builds(ctx, todo, ctx->d_tableFlags.p, 0));
+    CU(cudaMemcpyAsync(ctx->h_tableFlags.p, ctx->d_tableFlags.p, todo.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    ctx->pendingTables = todo;
+    return LVN_SUCCESS;
+}
+
+// Call with the context's stream synchronised.  *rebuilt = a table had to be rehashed: whatever read it
+// before (a batch that looked edges up through it) has to run again.
+static int validate_pending_tables(lvn_meshgen *ctx, bool *rebuilt)
+{
+    if (rebuilt) *rebuilt = false;
+    if (ctx->pendingTables.empty()) return LVN_SUCCESS;
+    std::vector<FieldEntry *> failed;
+    for (size_t i = 0; i < ctx->pendingTables.size(); i++)
+        if (ctx->h_tableFlags.p[i] != 0 || ctx->forceTableRetry) failed.push_back(ctx->pendingTables[i]);
+    ctx->pendingTables.clear();
+    if (failed.empty()) return LVN_SUCCESS;
+    if (rebuilt) *rebuilt = true;
+    return retry_table_builds(ctx, failed, 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -1604,10 +1678,11 @@ static int apply_csg_items(lvn_meshgen *ctx, const std::vector<CsgItem> &items)
         fe.numEdges = (int)(ctx->h_small.p[8 * i + 0] + ctx->h_small.p[8 * i + 1]);
         rebuild.push_back(&fe);
     }
-    LV(build_cuckoo_tables(ctx, rebuild));   // its host wait also covers hc's second upload
-    CU(cudaStreamSynchronize(st));
+    // no host wait here: the uploads above came from pageable memory (staged before the call returned), the
+    // tables' insert flags are read behind the next synchronisation of the stream (validate_pending_tables)
+    LV(build_cuckoo_tables(ctx, rebuild, !ctx->profiling));
+    if (ctx->profiling) { CU(cudaStreamSynchronize(st)); collect_stage_times(ctx); }
     CU(cudaGetLastError());
-    collect_stage_times(ctx);
     return LVN_SUCCESS;
 }
 

@@ -206,3 +206,32 @@ def test_batch_entry_points_replay_stored_ops(lc, oracle_mod, surface_cy):
     finally:
         lc.Compute_ClearCSGOperations()
         ctx.destroy(); world.close()
+
+
+def test_csg_deferred_hash_tables_are_validated(lc, oracle_mod, surface_cy, monkeypatch):
+    """an edit queues its hash-table builds without waiting for the insert flags; the batch behind it looks at
+    them before trusting what it meshed.  LVN_TEST_CUCKOO_RETRY=1 declares every first insertion failed: the
+    tables are rehashed with fresh parameters and the batch runs again -- results unchanged"""
+    monkeypatch.setenv("LVN_TEST_CUCKOO_RETRY", "1")
+    ctx = lc.Compute_MeshGenContext.create(64)
+    monkeypatch.delenv("LVN_TEST_CUCKOO_RETRY")
+    world = oracle_mod.World(image=lc.Compute_GetNoiseImage(), default_material=0, voxels_per_chunk=64)
+    try:
+        chunks = np.array([[cx * 256, surface_cy * 256, 0, 256] for cx in (-1, 0)], np.int32)
+        yc = surface_cy * 64 + 30.5
+        for spec in [(1, 1, 201, [-2.5, yc, 30.5], [11, 11, 11]), (0, 0, 2, [10.5, yc + 6, 40.5], [9, 4, 12])]:
+            op, oop = lc.CSGOperationInfo.make(*spec), oracle_mod.make_csg_op(*spec)
+            assert ctx.applyCSGOperationsBatch([op], chunks) == 0
+            for c in chunks:
+                world.apply_csg_operations([oop], [int(v) for v in c[:3]], 256)
+            res, V, T, S = batch_host(lc, ctx, chunks)
+            for c, r in zip(chunks, res):
+                mn = [int(v) for v in c[:3]]
+                ref = world.generate_chunk_mesh(mn, 256)
+                world.free_chunk_octree(mn, 256)
+                nv = ref["numNodes"] if ref["numTriangles"] > 0 else 0
+                assert r["numVertices"] == nv and r["numTriangles"] == ref["numTriangles"]
+                assert V[r["vertexOffset"]:r["vertexOffset"] + nv].tobytes() == ref["vertices"][:nv].tobytes()
+                assert np.array_equal(T["indices_"][r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]], ref["indices"])
+    finally:
+        ctx.destroy(); world.close()
