@@ -409,10 +409,111 @@ __device__ __forceinline__ float stress_density(const DensityParams &dp, float x
     return dp.param - f;
 }
 
+// ---------------------------------------------------------------------------
+// The stress density at two positions per thread (packed FP32, like terrain_height_x2): .x = position A,
+// .y = position B; every packed op is the IEEE binary32 operation of snoise3 / stress_density on each half,
+// so both halves are bit-identical to the scalar functions above (checked by the stress-field parity tests).
+// What stays per position: the simplex ordering (compares and selects), the two dependent gradient
+// fetches per corner, the gradient dot products (their operands come from different table rows) and
+// "0.6 - dot(P, P)", which the reference evaluates in double (simplex.cl:184-220).  A culled corner is
+// selected to +0 exactly as the scalar code returns it (no max() rewrite here).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float corner3_tail(const float4 *__restrict__ grad3, int ci, int cj, int ck, float r, float x, float y, float z,
+                                              float &t)
+{
+    // returns the gradient dot; t = (float)(0.6 - (double)r), culled corners are handled by the caller
+    const int col = __float_as_int(__ldg(&grad3[((cj & 255) << 8) | (ci & 255)]).w);
+    const float4 g = __ldg(&grad3[((ck & 255) << 8) | col]);
+    t = (float)(0.6 - (double)r);
+    return __fmaf_rn(g.z, z, __fmaf_rn(g.y, y, g.x * x));
+}
+
+__device__ __forceinline__ float2 corner3x2(const float4 *__restrict__ grad3, int ciA, int cjA, int ckA, int ciB, int cjB, int ckB,
+                                            float2 x, float2 y, float2 z, float2 nz)
+{
+    const float2 r = fma2(z, z, fma2(y, y, mul2(x, x, nz)));
+    float tA, tB;
+    const float dA = corner3_tail(grad3, ciA, cjA, ckA, r.x, x.x, y.x, z.x, tA);
+    const float dB = corner3_tail(grad3, ciB, cjB, ckB, r.y, x.y, y.y, z.y, tB);
+    const float2 t = make_float2(tA, tB);
+    const float2 t2 = mul2(t, t, nz);
+    const float2 n = mul2(mul2(t2, t2, nz), make_float2(dA, dB), nz);
+    return make_float2(tA < 0.f ? 0.f : n.x, tB < 0.f ? 0.f : n.y);
+}
+
+__device__ __forceinline__ float2 snoise3x2(const float4 *__restrict__ grad3, float2 px, float2 py, float2 pz, float2 nz)
+{
+    const float2 M = rep2(12582912.f);   // 1.5 * 2^23: floor(v) = fl_rd(v + M) - M for |v| < 2^22, see snoise2x2
+    const float2 s = mul2(add2(add2(px, py), pz), rep2(LVN_F3), nz);
+    const float2 mx = __fadd2_rd(add2(px, s), M), my = __fadd2_rd(add2(py, s), M), mz = __fadd2_rd(add2(pz, s), M);
+    const float2 ix = sub2(mx, M), iy = sub2(my, M), iz = sub2(mz, M);
+    // the low mantissa bits of the biased sums are floor(v) in two's complement (only the low 8 bits are used)
+    const int iiA = __float_as_int(mx.x), jjA = __float_as_int(my.x), kkA = __float_as_int(mz.x);
+    const int iiB = __float_as_int(mx.y), jjB = __float_as_int(my.y), kkB = __float_as_int(mz.y);
+    const float2 t = mul2(add2(add2(ix, iy), iz), rep2(LVN_G3), nz);
+    const float2 x0 = sub2(px, sub2(ix, t)), y0 = sub2(py, sub2(iy, t)), z0 = sub2(pz, sub2(iz, t));
+    // simplex ordering per position (simplex.cl:169-180).  The reference builds the offsets from floats
+    // (isXy = x0 < y0 ? 0 : 1, ...; ox = isXy + isXz, oy = 1 - isXy + isY, oz = 1 - isXz + 1 - isY, each in
+    // {0, 1, 2}; o2 = clamp(o, 0, 1), o1 = clamp(o - 1, 0, 1)): small integers, exact either way -- here
+    // in integers: o2 = (o >= 1), o1 = (o >= 2)
+    int o1[2][3], o2[2][3];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float xx = k ? x0.y : x0.x, yy = k ? y0.y : y0.x, zz = k ? z0.y : z0.x;
+        const int isXy = (xx < yy) ? 0 : 1, isXz = (xx < zz) ? 0 : 1, isY = (yy < zz) ? 0 : 1;
+        const int ox = isXy + isXz, oy = 1 - isXy + isY, oz = 2 - isXz - isY;
+        o2[k][0] = ox >= 1; o2[k][1] = oy >= 1; o2[k][2] = oz >= 1;
+        o1[k][0] = ox >= 2; o1[k][1] = oy >= 2; o1[k][2] = oz >= 2;
+    }
+    const float2 o1x = make_float2(o1[0][0] ? 1.f : 0.f, o1[1][0] ? 1.f : 0.f), o1y = make_float2(o1[0][1] ? 1.f : 0.f, o1[1][1] ? 1.f : 0.f),
+                 o1z = make_float2(o1[0][2] ? 1.f : 0.f, o1[1][2] ? 1.f : 0.f);
+    const float2 o2x = make_float2(o2[0][0] ? 1.f : 0.f, o2[1][0] ? 1.f : 0.f), o2y = make_float2(o2[0][1] ? 1.f : 0.f, o2[1][1] ? 1.f : 0.f),
+                 o2z = make_float2(o2[0][2] ? 1.f : 0.f, o2[1][2] ? 1.f : 0.f);
+    const float2 g1 = rep2(LVN_G3), g2 = rep2(2.f * LVN_G3), g3 = rep2(1.f - 3.f * LVN_G3);
+    const float2 n0 = corner3x2(grad3, iiA, jjA, kkA, iiB, jjB, kkB, x0, y0, z0, nz);
+    const float2 n1 = corner3x2(grad3, iiA + o1[0][0], jjA + o1[0][1], kkA + o1[0][2], iiB + o1[1][0], jjB + o1[1][1], kkB + o1[1][2],
+                                add2(sub2(x0, o1x), g1), add2(sub2(y0, o1y), g1), add2(sub2(z0, o1z), g1), nz);
+    const float2 n2 = corner3x2(grad3, iiA + o2[0][0], jjA + o2[0][1], kkA + o2[0][2], iiB + o2[1][0], jjB + o2[1][1], kkB + o2[1][2],
+                                add2(sub2(x0, o2x), g2), add2(sub2(y0, o2y), g2), add2(sub2(z0, o2z), g2), nz);
+    const float2 n3 = corner3x2(grad3, iiA + 1, jjA + 1, kkA + 1, iiB + 1, jjB + 1, kkB + 1,
+                                sub2(x0, g3), sub2(y0, g3), sub2(z0, g3), nz);
+    return mul2(rep2(32.f), add2(add2(add2(n0, n1), n2), n3), nz);
+}
+
+// stress_density at (xA, yA, zA) and (xB, yB, zB)
+__device__ __forceinline__ float2 stress_density_x2(const DensityParams &dp, float2 x, float2 y, float2 z)
+{
+    const float2 nz = rep2(dp.negZero);
+    float2 qx = mul2(x, rep2(1.f / 16.f), nz), qy = mul2(y, rep2(1.f / 16.f), nz), qz = mul2(z, rep2(1.f / 16.f), nz);
+    float2 f = rep2(0.f);
+    float amp = 1.f;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        const float2 n = snoise3x2(dp.grad3, qx, qy, qz, nz);
+        float2 r = sub2(rep2(1.f), make_float2(fabsf(n.x), fabsf(n.y)));
+        r = mul2(r, r, nz);
+        f = add2(f, mul2(r, rep2(amp), nz));
+        qx = mul2(qx, rep2(2.f), nz);
+        qy = mul2(qy, rep2(2.f), nz);
+        qz = mul2(qz, rep2(2.f), nz);
+        amp *= 0.5f;
+    }
+    f = mul2(f, rep2(1.f / 1.875f), nz);
+    return sub2(rep2(dp.param), f);
+}
+
 __device__ __forceinline__ float density3(const DensityParams &dp, float x, float y, float z)
 {
     if (dp.kind == 1) return stress_density(dp, x, y, z);
     return y - terrain_height(dp.grad2, x, z);
+}
+
+// density3 at two positions
+__device__ __forceinline__ float2 density3_x2(const DensityParams &dp, float2 x, float2 y, float2 z)
+{
+    if (dp.kind == 1) return stress_density_x2(dp, x, y, z);
+    const float2 h = terrain_height_x2(grad_tables(dp), dp.negZero, x, z);
+    return make_float2(y.x - h.x, y.y - h.y);
 }
 
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a + (b - a) * t; }
