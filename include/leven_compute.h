@@ -183,6 +183,12 @@ typedef struct lvn_stage_dump {
     float    *nodePositions; /* 4N (octree.cl:327-330) */
     float    *nodeNormals;   /* 4N (octree.cl:303-311) */
 } lvn_stage_dump;
+/* qef_solve (qef.cl:239-256) on caller-supplied QEFData records (16 floats each: ATA[6], pad[2], ATb[4],
+ * masspoint[4], qef.cl:7-14), positions in chunk-local units (worldSpaceOffset 0, scale 4): the unit test
+ * of k_solve's arithmetic.  packed = 1 runs the production form (two nodes per thread, packed FP32 with
+ * written-out division / square-root sequences), packed = 0 the plain scalar form. */
+int lvn_debug_solve_qefs(int packed, int n, const float *qefs16, float *positions4);
+
 /* runs the path for one chunk with cold octree cache semantics and copies every stage out */
 int lvn_meshgen_debug_dump_chunk(lvn_meshgen *ctx, const int32_t min[3], int size, lvn_stage_dump *dump);
 

@@ -112,6 +112,7 @@ ABI = {
     "lvn_meshgen_generate_batch_device": (_I, [_P, _I, _P, _P, _P]),
     "lvn_meshgen_apply_csg_operations_batch": (_I, [_P, _P, _I, _I, _P]),
     "lvn_meshgen_debug_dump_chunk": (_I, [_P, _P, _I, _P]),
+    "lvn_debug_solve_qefs": (_I, [_I, _I, _P, _P]),
     "lvn_meshgen_set_profiling": (_I, [_P, _I]),
     "lvn_meshgen_get_stats": (_I, [_P, _P, _I]),
     "lvn_meshgen_set_stream": (_I, [_P, _P]),
@@ -468,6 +469,15 @@ def GlobalMeshOffsets(gathered, world_size, per_rank, num_chunks, counts, offset
     """lvn_global_mesh_offsets into caller-owned int64 arrays counts[n, 3], offsets[n, 3], totals[3]"""
     return lib().lvn_global_mesh_offsets(_ptr(gathered), int(world_size), int(per_rank), int(num_chunks),
                                          _ptr(counts), _ptr(offsets), _ptr(totals))
+
+
+def DebugSolveQEFs(qefs16, packed=True):
+    """lvn_debug_solve_qefs: qefs16 float32[n, 16] (QEFData layout) -> positions float32[n, 4]"""
+    q = np.ascontiguousarray(qefs16, np.float32).reshape(-1, 16)
+    out = np.zeros((len(q), 4), np.float32)
+    rc = lib().lvn_debug_solve_qefs(int(bool(packed)), len(q), _ptr(q), _ptr(out))
+    assert rc == 0, GetCLErrorString(rc)
+    return out
 
 
 def FindNextPrime(n):

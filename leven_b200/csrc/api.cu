@@ -1877,6 +1877,25 @@ extern "C" int lvn_meshgen_generate_chunk_mesh(lvn_meshgen *ctx, const int32_t m
     return LVN_SUCCESS;
 }
 
+extern "C" int lvn_debug_solve_qefs(int packed, int n, const float *qefs16, float *positions4)
+{
+    if (!g.initialised) return LVN_ERR_NOT_INITIALISED;
+    if (n < 0 || (n > 0 && (!qefs16 || !positions4))) return LVN_ERR_INVALID_VALUE;
+    if (n == 0) return LVN_SUCCESS;
+    DevBuf<float> d_q;
+    DevBuf<float4> d_p;
+    int rc = LVN_SUCCESS;
+    if ((rc = d_q.reserve((size_t)n * 16)) == LVN_SUCCESS && (rc = d_p.reserve(n)) == LVN_SUCCESS) {
+        if (cudaMemcpy(d_q.p, qefs16, (size_t)n * 64, cudaMemcpyHostToDevice) != cudaSuccess) rc = LVN_ERR_CUDA;
+        if (rc == LVN_SUCCESS) {
+            launch_solve_debug(packed, n, d_q.p, d_p.p, 0);
+            if (cudaMemcpy(positions4, d_p.p, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LVN_ERR_CUDA;
+        }
+    }
+    d_q.release(); d_p.release();
+    return rc;
+}
+
 // ---------------------------------------------------------------------------
 // per-stage dump
 // ---------------------------------------------------------------------------

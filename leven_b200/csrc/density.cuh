@@ -452,18 +452,17 @@ __device__ __forceinline__ float2 snoise3x2(const float4 *__restrict__ grad3, fl
     const int iiB = __float_as_int(mx.y), jjB = __float_as_int(my.y), kkB = __float_as_int(mz.y);
     const float2 t = mul2(add2(add2(ix, iy), iz), rep2(LVN_G3), nz);
     const float2 x0 = sub2(px, sub2(ix, t)), y0 = sub2(py, sub2(iy, t)), z0 = sub2(pz, sub2(iz, t));
-    // simplex ordering per position (simplex.cl:169-180).  The reference builds the offsets from floats
-    // (isXy = x0 < y0 ? 0 : 1, ...; ox = isXy + isXz, oy = 1 - isXy + isY, oz = 1 - isXz + 1 - isY, each in
-    // {0, 1, 2}; o2 = clamp(o, 0, 1), o1 = clamp(o - 1, 0, 1)): small integers, exact either way -- here
-    // in integers: o2 = (o >= 1), o1 = (o >= 2)
+    // simplex ordering per position (simplex.cl:169-180), as the reference writes it; the offsets are exactly 0 or 1
     int o1[2][3], o2[2][3];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const float xx = k ? x0.y : x0.x, yy = k ? y0.y : y0.x, zz = k ? z0.y : z0.x;
-        const int isXy = (xx < yy) ? 0 : 1, isXz = (xx < zz) ? 0 : 1, isY = (yy < zz) ? 0 : 1;
-        const int ox = isXy + isXz, oy = 1 - isXy + isY, oz = 2 - isXz - isY;
-        o2[k][0] = ox >= 1; o2[k][1] = oy >= 1; o2[k][2] = oz >= 1;
-        o1[k][0] = ox >= 2; o1[k][1] = oy >= 2; o1[k][2] = oz >= 2;
+        const float isXy = (xx < yy) ? 0.f : 1.f, isXz = (xx < zz) ? 0.f : 1.f, isY = (yy < zz) ? 0.f : 1.f;
+        float ox = isXy + isXz, oy = 1.f - isXy, oz = 1.f - isXz;
+        oy += isY;
+        oz += 1.f - isY;
+        o2[k][0] = (int)clamp01(ox); o2[k][1] = (int)clamp01(oy); o2[k][2] = (int)clamp01(oz);
+        o1[k][0] = (int)clamp01(ox - 1.f); o1[k][1] = (int)clamp01(oy - 1.f); o1[k][2] = (int)clamp01(oz - 1.f);
     }
     const float2 o1x = make_float2(o1[0][0] ? 1.f : 0.f, o1[1][0] ? 1.f : 0.f), o1y = make_float2(o1[0][1] ? 1.f : 0.f, o1[1][1] ? 1.f : 0.f),
                  o1z = make_float2(o1[0][2] ? 1.f : 0.f, o1[1][2] ? 1.f : 0.f);

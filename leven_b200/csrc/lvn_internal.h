@@ -137,6 +137,8 @@ void launch_leaves(const DensityParams &dp, const Dims &d, const ChunkDesc *desc
 void launch_solve(const ChunkDesc *descs, LaneArenas lane, const void *qefScratch, lvn_mesh_vertex *vertices,
                   lvn_seam_node_info *seams, float4 *dbgPositions, cudaStream_t s);
 
+void launch_solve_debug(int packed, int n, const float *qef16, float4 *out, cudaStream_t s);
+
 // ---- launchers (kernels_csg.cu) -------------------------------------------
 struct CsgOpDev {          // CSGOperation + host-computed cos/sin of rotateY
     int type, shape, material, pad;
