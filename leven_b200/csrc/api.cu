@@ -503,6 +503,8 @@ struct lvn_meshgen {
     PinBuf<unsigned int> h_small;
 
     ArenaCounters lastCounters = {};   // totals over the lanes of the last batch
+    int hintChunks = 0;                // what the last batch of this many chunks produced: a batch list repeats
+    unsigned int hintNodes = 0, hintNonEmpty = 0;   // in steady state, and a sparse one wants fewer lanes
     int lastN = 0;
 
     // lanes of a batch (run_batch): independent slices of the chunk list, each a chain
@@ -783,6 +785,12 @@ static void choose_pipeline(const lvn_meshgen *ctx, int n, const BatchOpts &opts
         // load, profiles/r01h_notes.md)
         lanes = n >= 128 ? (hostPath ? 8 : 2) : 1;
         streams = 2;
+        // a lane costs ~40 us of launches and kernel tails whatever it holds: a batch that was sparse the last
+        // time (one rank's share of the sweep at 8 GPUs: 512 chunks, 48 with surface) runs in fewer lanes
+        if (lanes > 1 && ctx->hintChunks == n) {
+            if (hostPath) lanes = (int)std::max(1u, std::min(8u, ctx->hintNodes / 50000u));
+            else if (ctx->hintNonEmpty < 80u) lanes = 1;
+        }
     }
     // per-stage event timing and the stage dumps want one kernel at a time on one stream
     if (ctx->profiling || opts.debug || opts.singleLane) lanes = 1;
@@ -1166,6 +1174,7 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
         }
         if (!tot.overflow) {
             ctx->lastCounters = tot;
+            ctx->hintChunks = n; ctx->hintNodes = tot.nodes; ctx->hintNonEmpty = tot.nonEmpty;
             int64_t ey = 0;
             for (int k = 0; k < S; k++)
                 for (int p = ctx->laneFirst[k]; p < ctx->laneFirst[k + 1]; p++) ey += ctx->h_hdrs.p[p + k].Ey;
