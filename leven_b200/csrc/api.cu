@@ -963,6 +963,10 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
 
     // ---- S1 for the whole batch: the column sets are shared between the lanes ----
     if (numColSets) {
+        // stage timing: the interval's first event would be stamped by the copy engine that delivered the batch
+        // head, and the hand-over to the compute engine (~30 us) would be booked on k_columns (14 us under
+        // ncu); a one-thread kernel in front makes the compute engine stamp it
+        if (ctx->profiling) launch_publish(ctx->d_hdrs.p, ctx->d_hdrs.p, 0, st, true);
         StageTimer t(ctx, LVN_STAGE_COLUMNS, 1);
         launch_columns(dp, d, d_colOrigins, numColSets, ctx->d_heights.p, d_colMin, d_colMax, st);
         ctx->stats.terrainEvals += (int64_t)numColSets * (int64_t)FF;

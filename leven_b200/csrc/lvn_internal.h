@@ -125,7 +125,7 @@ void launch_rows(const Dims &d, const ChunkDesc *descs, int first, int n, const 
                  const int *colMin, const int *colMax, ChunkHdr *hdrs, ChunkHdr *hostHdrs, ChunkScratch ws,
                  LaneArenas lane, int *candidateList /* [n chunks of the batch] */, cudaStream_t s);
 // hostHdrs / hostCounters may be null: launch_publish then mirrors the lane's header slots
-void launch_publish(const ChunkHdr *devHdrs, ChunkHdr *hostHdrs, int count, cudaStream_t s);
+void launch_publish(const ChunkHdr *devHdrs, ChunkHdr *hostHdrs, int count, cudaStream_t s, bool evenIfEmpty = false);
 void launch_hermite(const DensityParams &dp, const Dims &d, const ChunkDesc *descs, const ChunkHdr *hdrs,
                     ChunkScratch ws, LaneArenas lane, const float *heights, int *edgeKeys, float4 *edgeInfo,
                     int2 *xzList, cudaStream_t s);
