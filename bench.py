@@ -294,11 +294,13 @@ def stage_table(stats, K, nchunks, col_sets, kind, fp32_peak, hbm_peak, prof=Non
             s["frac"] = s["achieved_tflops"] / fp32_peak if fp32_peak else None
         else:
             s["frac"] = s["achieved_gbs"] / hbm_peak
-        key = {"k_columns": "columns", "k_rows": "rows", "k_hermite_terrain": "hermite", "k_leaves": "leaves"}.get(s["kernel"], "")
+        key = {"k_columns": "columns", "k_rows": "rows", "k_hermite_terrain": "hermite", "k_leaves": "leaves", "k_solve": "solve"}.get(s["kernel"], "")
         inst = prof.get(key + "_warp_inst_per_launch")
         if inst and s["ms"] > 0 and kind == "terrain":
             s["warp_inst_per_launch_ncu"] = inst
             s["issue_frac"] = inst / (s["ms"] * 1e-3) / issue_peak
+        if kind == "terrain" and prof.get(key + "_dram_bytes_per_launch") is not None:
+            s["traffic_dram_bytes_ncu"] = prof[key + "_dram_bytes_per_launch"]
     counts = {"edges": E, "edges_y": Ey, "vertices": N, "triangles": T, "seam_nodes": S, "non_empty_chunks": NE}
     return stages, counts
 

@@ -23,7 +23,13 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_xu.sum",
         "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_lsu.sum",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max",
-        "smsp__cycles_active.avg"]
+        "smsp__cycles_active.avg",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
 
@@ -47,7 +53,9 @@ def raw(rep):
     return d
 
 
-def hot_lines(rep, top=12):
+def hot_lines(rep, top=14):
+    """per CUDA source line: warp instructions executed and stall samples, summed over the SASS instructions
+    ncu lists under that line (the cuda,sass view carries the counters on the SASS rows only)"""
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -56,19 +64,25 @@ def hot_lines(rep, top=12):
         return []
     h = rows[hi[0]]
     cs, ci = h.index("# Samples"), h.index("Instructions Executed")
-    agg, tot = [], 0.0
+    agg, cur = {}, None
     for r in rows[hi[0] + 1:]:
-        if len(r) <= ci or not r[0].strip().isdigit():
+        if len(r) <= max(cs, ci):
+            continue
+        if r[0] != "":
+            cur = (r[0], r[1].strip()[:100])
+            agg.setdefault(cur, [0.0, 0.0])
+            continue
+        if cur is None or r[2] in ("", "..."):
             continue
         try:
-            v, ins = float(r[cs]), float(r[ci])
+            agg[cur][0] += float(r[cs]); agg[cur][1] += float(r[ci])
         except ValueError:
             continue
-        agg.append((v, ins, int(r[0]), r[1].strip()[:100]))
-        tot += v
-    agg.sort(reverse=True)
-    return [{"pct_samples": round(100 * v / tot, 1), "warp_inst": int(ins), "line": ln, "src": src}
-            for v, ins, ln, src in agg[:top]]
+    tot = sum(v[0] for v in agg.values()) or 1.0
+    tin = sum(v[1] for v in agg.values()) or 1.0
+    best = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
+    return [{"pct_samples": round(100 * v[0] / tot, 1), "pct_inst": round(100 * v[1] / tin, 1), "warp_inst": int(v[1]),
+             "line": int(k[0]) if k[0].isdigit() else 0, "src": k[1]} for k, v in best]
 
 
 def main():
@@ -81,7 +95,7 @@ def main():
         d["hot_source_lines"] = hot_lines(rep)
         summary.append(d)
         t = d.get("dram__bytes_read.sum [B]", 0.0) + d.get("dram__bytes_write.sum [B]", 0.0)
-        for key in ("hermite", "leaves", "rows", "columns"):
+        for key in ("hermite", "leaves", "rows", "columns", "solve"):
             if "k_" + key in d["kernel"]:
                 traffic[key + "_dram_bytes_per_launch"] = t
                 # executed warp instructions of that launch: bench.py's issue-slot fraction
@@ -94,7 +108,7 @@ def main():
                 if k not in ("kernel", "report", "hot_source_lines"):
                     f.write(f"   {k:72s} {v:,.3f}\n")
             for hl in d["hot_source_lines"]:
-                f.write(f"   {hl['pct_samples']:5.1f}% samples  inst={hl['warp_inst']:>9d}  L{hl['line']}: {hl['src']}\n")
+                f.write(f"   {hl['pct_inst']:5.1f}% inst {hl['pct_samples']:5.1f}% samples  L{hl['line']}: {hl['src']}\n")
             f.write("\n")
     traffic["source"] = f"profiles/{tag}_summary.json (ncu --set full --clock-control none, one launch each)"
     json.dump(traffic, open(os.path.join(here, "latest_traffic.json"), "w"), indent=1)
