@@ -477,6 +477,17 @@ def main():
         torch.cuda.synchronize()
         link_ms.append(a.elapsed_time(b))
     link_ms = float(np.median(link_ms[2:]))
+    # the same copy 24 times back to back on every rank at once: the SUSTAINED rate of this rank's link while the
+    # others keep theirs busy too -- what the end-to-end step sees (a one-off copy hides shared uplinks)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(24):
+        link_host.copy_(flush[:link_bytes], non_blocking=True)
+    b.record(stream)
+    torch.cuda.synchronize()
+    link_sustained_ms = a.elapsed_time(b) / 24.0
+    barrier()
     # ---- per-kernel durations: the same batch with one lane on one stream, so that every kernel
     #      runs alone between its two CUDA events (in the timed regions above kernels of
     #      different lanes overlap and an event pair would also time its neighbours) ----
@@ -493,7 +504,8 @@ def main():
     e2e_ms_max = max_over_ranks(e2e_ms)
     value = world_size * nchunks * args.steps * inner / (dev_ms_max * 1e-3)
     e2e_value = world_size * nchunks * args.steps * inner_e2e / (e2e_ms_max * 1e-3)
-    per_rank = gather_ranks([e2e_ms / (args.steps * inner_e2e), dev_ms / (args.steps * inner), link_bytes / link_ms / 1e6])
+    per_rank = gather_ranks([e2e_ms / (args.steps * inner_e2e), dev_ms / (args.steps * inner), link_bytes / link_ms / 1e6,
+                             link_bytes / link_sustained_ms / 1e6])
 
     # =========================================================================================
     # configs.sweep: configs[4], 4096 chunks, chunk i -> GPU i mod N, count gather inside the step
@@ -590,7 +602,9 @@ def main():
                                  "time (rank 0's figure): the PCIe floor of the batch on this box at this number of GPUs"},
                 "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)"},
         "per_rank": {"e2e_ms_per_batch": [r[0] for r in per_rank], "device_ms_per_batch": [r[1] for r in per_rank],
-                     "link_gbs": [r[2] for r in per_rank], "pinned_cores_rank0": pinned_cores},
+                     "link_gbs": [r[2] for r in per_rank], "link_gbs_sustained": [r[3] for r in per_rank],
+                     "link_floor_ms_per_batch": [round(link_bytes / (r[3] * 1e6), 4) for r in per_rank],
+                     "pinned_cores_rank0": pinned_cores},
         "gpu_launches": int(sum(run_stats["launches"].values())),
         "clocks": clocks,
         "roofline": {"kernel": "k_hermite_terrain (FindEdgeIntersectionInfo)", "bound": "fp32",

@@ -55,6 +55,12 @@ struct ArenaCounters {
 // empty chunks cost nothing.
 struct TileRef { int chunk, first; };
 constexpr int LVN_TILE = 128;
+// edges per block of the Hermite kernels.  Measured (ring): 128 edges 183.4 us, 256 edges 186.9 us -- although
+// 256 edges fill the 256-thread block's search rounds better (720 items = 2.8 rounds against 360 = 1.4), the
+// other resident blocks fill those gaps already and the larger tile only lengthens the tail.
+#ifndef LVN_ETILE
+#define LVN_ETILE 128
+#endif
 
 struct ArenaCaps { unsigned int edges, nodes, quads, seams; };
 
