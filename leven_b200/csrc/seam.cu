@@ -41,7 +41,8 @@ constexpr unsigned int SEAM_INTERNAL = 0xfffffffeu;
 constexpr unsigned int SEAM_NONE = 0xffffffffu;
 // A seam of the default terrain has a few hundred leaves: its cell table, its sort keys and its
 // quad flags fit the block's shared memory, and only larger seams use the global scratch slices.
-constexpr int SEAM_SMEM_TABLE = 4096;        // entries (8 B key + 4 B value); used while leaves * levels <= 3/4 of it
+constexpr int SEAM_SMEM_TABLE = 16384;       // entries (8 B key + 4 B value): a seam owns its SM (1024 threads at 64 registers), so it may as well
+                                             // own its shared memory: 208 KB; seams of up to 1024 leaves x 8 levels keep their table on chip
 constexpr int SEAM_SMEM_KEYS = SEAM_SMEM_TABLE;   // selected leaves whose sort keys fit (they lie where the table's keys will)
 constexpr int SEAM_SMEM_WORDS = 1024;        // quad flag words: 2730 leaves * 12 edges / 32
 constexpr size_t SEAM_SMEM_BYTES = (size_t)SEAM_SMEM_TABLE * 12 + (size_t)SEAM_SMEM_WORDS * 16;
@@ -303,10 +304,14 @@ k_seam(const SeamJobDev *__restrict__ jobs, const int *__restrict__ launchOrder,
 
     SPHASE(1);
     // ---- 3. leaves and all their ancestors into the table (Octree_ConstructUpwards) ----
-    const bool tableInSmem = !forceGlobal && (long long)n * (job.rootLog2 + 1) * 4 <= (long long)SEAM_SMEM_TABLE * 3;
+    // table size from the seam's own leaf count (load <= 1/2), not from its candidates' (the host's bound, 3.3 x
+    // as many): the zero fill of candidate-sized global tables was 63 MB of the launch's 66 MB of DRAM writes
+    unsigned int tsize = 64u;
+    while ((long long)tsize < (long long)n * (job.rootLog2 + 1) * 2) tsize <<= 1;
+    const bool tableInSmem = !forceGlobal && tsize <= (unsigned int)SEAM_SMEM_TABLE;
     unsigned long long *tkeys = tableInSmem ? s_tkeys : ws.tableKeys + job.tableOffset;
     unsigned int *tvals = tableInSmem ? s_tvals : ws.tableVals + job.tableOffset;
-    const unsigned int tmask = tableInSmem ? (unsigned int)(SEAM_SMEM_TABLE - 1) : job.tableMask;
+    const unsigned int tmask = tableInSmem ? tsize - 1u : min(job.tableMask, tsize - 1u);
     for (unsigned int i = tid; i <= tmask; i += SEAM_BLOCK) tkeys[i] = 0ull;
     __syncthreads();
     for (int i = tid; i < n; i += SEAM_BLOCK) {
