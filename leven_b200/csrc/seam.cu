@@ -490,6 +490,17 @@ using namespace lvn;
 
 extern "C" const char *lvn_seam_last_error(void) { return g_seamError; }
 
+// trianglesPerCandidate: the internal triangle scratch of a seam.  A leaf owns at most 12 quads = 24 triangles;
+// the default meshes average under one triangle per candidate node, so the scratch is sized for 8 and a seam
+// that needs more makes the whole call run once more at the true bound (the limit was internal,
+// so the caller could not fix a capacity error by passing larger arenas).
+static int seam_mesh_generate(int voxelsPerChunk, int numSeams, const lvn_seam_job *jobs,
+                              const lvn_seam_neighbour *neighbours, int numNeighbours,
+                              const lvn_seam_node_info *seamNodes, int numSeamNodes,
+                              lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                              lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                              lvn_seam_result *results, int trianglesPerCandidate);
+
 extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, const lvn_seam_job *jobs,
                                             const lvn_seam_neighbour *neighbours, int numNeighbours,
                                             const lvn_seam_node_info *seamNodes, int numSeamNodes,
@@ -497,6 +508,20 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
                                             lvn_mesh_triangle *triangles, int64_t triangleCapacity,
                                             lvn_seam_result *results)
 {
+    int first = 8;
+    if (const char *e = getenv("LVN_SEAM_TRIANGLES_PER_CANDIDATE")) first = std::max(0, std::min(24, atoi(e)));   // tests: force the retry
+    return seam_mesh_generate(voxelsPerChunk, numSeams, jobs, neighbours, numNeighbours, seamNodes, numSeamNodes, vertices,
+                              vertexCapacity, triangles, triangleCapacity, results, first);
+}
+
+static int seam_mesh_generate(int voxelsPerChunk, int numSeams, const lvn_seam_job *jobs,
+                              const lvn_seam_neighbour *neighbours, int numNeighbours,
+                              const lvn_seam_node_info *seamNodes, int numSeamNodes,
+                              lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                              lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                              lvn_seam_result *results, int trianglesPerCandidate)
+{
+    const size_t TPC = (size_t)trianglesPerCandidate;
     if (numSeams < 0 || voxelsPerChunk <= 0 || (numSeams > 0 && (!jobs || !results))) return LVN_ERR_INVALID_VALUE;
     if (numSeams == 0) return LVN_SUCCESS;
     int dev = 0;
@@ -532,7 +557,7 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
         while (cap < (size_t)cand * (size_t)(lg + 1) * 2) cap <<= 1;
         d.tableOffset = totalTable; d.tableMask = (unsigned int)(cap - 1);
         d.vertexBase = (int)totalCand; d.vertexCap = cand;
-        d.triangleBase = (int)(totalCand * 8); d.triangleCap = cand * 8;
+        d.triangleBase = (int)(totalCand * TPC); d.triangleCap = cand * (int)TPC;
         totalCand += (size_t)cand;
         totalTable += cap;
     }
@@ -545,8 +570,8 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
                  oKey = take(8 * candPad), oSrc = take(4 * candPad), oSorted = take(sizeof(int4) * candPad), oCnt = take(4 * candPad),
                  oQuads = take(sizeof(int4) * 12 * candPad), oTK = take(8 * std::max<size_t>(totalTable, 1)),
                  oTV = take(4 * std::max<size_t>(totalTable, 1)), oV = take(sizeof(lvn_mesh_vertex) * candPad),
-                 oT = take(sizeof(int) * 3 * 8 * candPad), oRes = take(sizeof(int4) * numSeams),
-                 oPack = take(sizeof(int4) * numSeams), oOrder = take(sizeof(int) * numSeams), oPV = take(sizeof(lvn_mesh_vertex) * candPad), oPT = take(sizeof(int) * 3 * 8 * candPad);
+                 oT = take(sizeof(int) * 3 * TPC * candPad), oRes = take(sizeof(int4) * numSeams),
+                 oPack = take(sizeof(int4) * numSeams), oOrder = take(sizeof(int) * numSeams), oPV = take(sizeof(lvn_mesh_vertex) * candPad), oPT = take(sizeof(int) * 3 * TPC * candPad);
     if (off > g_seam.blobCap) {
         if (g_seam.d_blob) SCU(cudaFree(g_seam.d_blob));
         g_seam.d_blob = nullptr; g_seam.blobCap = 0;
@@ -593,6 +618,14 @@ extern "C" int lvn_seam_mesh_generate_batch(int voxelsPerChunk, int numSeams, co
 
     // ---- pack the meshes into the caller's arenas, in job order: offsets on the host, one pack
     //      kernel, two copies ----
+    if (trianglesPerCandidate < 24) {
+        // a seam whose triangles did not fit the internal scratch (its vertices always do: one per candidate at most)
+        bool internal = false;
+        for (int s = 0; s < numSeams; s++) internal = internal || (res[s].w && res[s].y > jd[s].triangleCap);
+        if (internal)
+            return seam_mesh_generate(voxelsPerChunk, numSeams, jobs, neighbours, numNeighbours, seamNodes, numSeamNodes, vertices,
+                                      vertexCapacity, triangles, triangleCapacity, results, 24);
+    }
     std::vector<int4> pack(numSeams);
     int64_t hv = 0, ht = 0;
     int rc = LVN_SUCCESS;

@@ -132,3 +132,18 @@ def test_gpu_seam_edge_cases(lc, seams_of, surface_cy):
     bad = np.zeros(1, c.SeamJob); bad[0]["hostSize"] = 300; bad[0]["numNeighbours"] = 0
     r = np.zeros(1, c.SeamResult)
     assert c.lib().lvn_seam_mesh_generate_batch(64, 1, c._ptr(bad), None, 0, None, 0, None, 0, None, 0, c._ptr(r)) == c.LVN_ERR_INVALID_VALUE
+
+
+@pytest.mark.gpu
+def test_gpu_seam_internal_triangle_scratch_retries(lc, seams_of, surface_cy, monkeypatch):
+    """the triangle scratch of a seam is sized for 8 triangles per candidate node; a seam that needs more makes
+    the call run again at the true bound of 24 instead of failing with a capacity error the caller cannot
+    cure.  LVN_SEAM_TRIANGLES_PER_CANDIDATE=0 makes every seam with a triangle take that path."""
+    jobs = S.build_jobs(S.SCENARIOS["uniform_lod0"](surface_cy), seams_of)
+    rc0, meshes0, res0 = lc.GenerateClipmapSeamMeshes(64, jobs)
+    monkeypatch.setenv("LVN_SEAM_TRIANGLES_PER_CANDIDATE", "0")
+    rc1, meshes1, res1 = lc.GenerateClipmapSeamMeshes(64, jobs)
+    assert rc0 == 0 and rc1 == 0, lc.lib().lvn_seam_last_error()
+    assert sum(len(t) for _, t in meshes0) > 1000
+    for (v0, t0), (v1, t1) in zip(meshes0, meshes1):
+        assert v0.tobytes() == v1.tobytes() and t0.tobytes() == t1.tobytes()
