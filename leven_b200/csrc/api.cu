@@ -483,6 +483,7 @@ struct lvn_meshgen {
     std::vector<FieldEntry *> pendingTables;
     DevBuf<unsigned int> d_tableFlags;
     PinBuf<unsigned int> h_tableFlags;
+    int lookahead = 2;                     // host path: lanes queued ahead of the one whose copies are being queued (LVN_LOOKAHEAD)
     bool forceTableRetry = false;          // LVN_TEST_CUCKOO_RETRY=1: treat every first insertion as failed (tests)
     DevBuf<CsgOpDev> d_ops;
     DevBuf<CsgChunk> d_csgChunks;
@@ -575,6 +576,7 @@ extern "C" lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk)
     if (const char *e = getenv("LVN_STREAMS")) ctx->cfgStreams = atoi(e);
     if (const char *e = getenv("LVN_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char *e = getenv("LVN_TEST_CUCKOO_RETRY")) ctx->forceTableRetry = atoi(e) != 0;
+    if (const char *e = getenv("LVN_LOOKAHEAD")) ctx->lookahead = std::max(1, atoi(e));
     return ctx;
 }
 
@@ -1098,7 +1100,7 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
             int64_t hv = 0, ht = 0, hs = 0;
             int issued = 0;
             for (int k = 0; k < S; k++) {
-                while (issued < S && issued < k + 2) LV(enqueue_lane(issued++));
+                while (issued < S && issued < k + ctx->lookahead) LV(enqueue_lane(issued++));
                 if (overflow || hostFull) continue;   // keep issuing: the retry needs every lane's counts
                 const double w0 = ctx->trace ? host_now_us() : 0.0;
                 CU(cudaEventSynchronize(ctx->evPub[k]));
