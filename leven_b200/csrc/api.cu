@@ -270,6 +270,7 @@ static int upload_noise_image()
 {
     std::vector<float2> g2(257 * 257);   // + one wrapped column and row (density.cuh: LVN_G2PITCH)
     std::vector<float4> g3(65536);
+    std::vector<uint8_t> perm3(65536);   // the first lookup of a snoise3 corner wants the column alone: a byte table behind the gradients
     for (int r = 0; r < 257; r++)
         for (int c = 0; c < 257; c++) {
             const uint8_t *px = &g.image[(size_t)(((r & 255) << 8) | (c & 255)) * 4];
@@ -281,15 +282,17 @@ static int upload_noise_image()
         // NEAREST + REPEAT lands on column v, and on column 0 for v = 255 (simplex.cl:184-185)
         const int col = px[3] == 255 ? 0 : (int)px[3];
         g3[t] = make_float4(unorm_grad(px[0]), unorm_grad(px[1]), unorm_grad(px[2]), int_as_float_host(col));
+        perm3[t] = (uint8_t)col;
     }
     if (!g.d_grad2) CU(cudaMalloc((void **)&g.d_grad2, g2.size() * sizeof(float2)));
-    if (!g.d_grad3) CU(cudaMalloc((void **)&g.d_grad3, 65536 * sizeof(float4)));
+    if (!g.d_grad3) CU(cudaMalloc((void **)&g.d_grad3, 65536 * sizeof(float4) + 65536));
     std::vector<float> planes(2 * g2.size());
     for (size_t i = 0; i < g2.size(); i++) { planes[i] = g2[i].x; planes[g2.size() + i] = g2[i].y; }
     if (!g.d_grad2x) CU(cudaMalloc((void **)&g.d_grad2x, planes.size() * sizeof(float)));
     CU(cudaMemcpy(g.d_grad2x, planes.data(), planes.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_grad2, g2.data(), g2.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_grad3, g3.data(), 65536 * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g.d_grad3 + 65536, perm3.data(), 65536, cudaMemcpyHostToDevice));
     return LVN_SUCCESS;
 }
 
@@ -476,7 +479,9 @@ struct lvn_meshgen {
     DevBuf<float> d_dbgQefs;
     DevBuf<float4> d_dbgPos, d_dbgNrm;
     // csg scratch
-    DevBuf<unsigned int> d_touched, d_csgCounts;
+    DevBuf<unsigned int> d_touched, d_csgCounts;   // d_touched: an edit's counters, ticket and touched-edge bitmaps
+    DevBuf<unsigned char> d_csgStage;              // an edit's [chunks | ops]
+    PinBuf<unsigned char> h_csgStage;
     // hash tables built without waiting for their insert flags (apply_csg_items): the flags land in
     // h_tableFlags behind the stream's next synchronisation, run_batch looks at them before it trusts
     // a result that read those tables (validate_pending_tables)
@@ -485,8 +490,6 @@ struct lvn_meshgen {
     PinBuf<unsigned int> h_tableFlags;
     int lookahead = 2;                     // host path: lanes queued ahead of the one whose copies are being queued (LVN_LOOKAHEAD)
     bool forceTableRetry = false;          // LVN_TEST_CUCKOO_RETRY=1: treat every first insertion as failed (tests)
-    DevBuf<CsgOpDev> d_ops;
-    DevBuf<CsgChunk> d_csgChunks;
     // simplified batch (lvn_meshgen_generate_simplified_batch)
     DevBuf<int4> d_simpRes;
     DevBuf<int2> d_packOff;
@@ -596,7 +599,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
-    ctx->d_ops.release(); ctx->d_csgChunks.release(); ctx->d_tableFlags.release(); ctx->h_tableFlags.release();
+    ctx->d_csgStage.release(); ctx->h_csgStage.release(); ctx->d_tableFlags.release(); ctx->h_tableFlags.release();
     ctx->d_simpRes.release(); ctx->d_packOff.release(); ctx->d_packV.release(); ctx->d_packP.release(); ctx->d_packT.release();
     ctx->h_simpRes.release(); ctx->h_packOff.release();
     if (ctx->simpStreamB) cudaStreamDestroy(ctx->simpStreamB);
@@ -1467,13 +1470,22 @@ static int enqueue_table_builds(lvn_meshgen *ctx, const std::vector<FieldEntry *
 {
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(d_flags, 0, todo.size() * sizeof(unsigned int), st));
-    for (size_t i = 0; i < todo.size(); i++) {
-        FieldEntry *fe = todo[i];
-        draw_cuckoo_params(fe->params);
-        launch_fill_u64(fe->d_table, fe->prime, ~0ull, st);
-        launch_cuckoo_insert((const unsigned int *)fe->d_keys, (unsigned int)fe->numEdges, fe->d_table, fe->prime, fe->params,
-                             d_flags + i, st);
-        fe->cuckooRetries = attempt;
+    for (size_t first = 0; first < todo.size(); first += LVN_TABLE_JOBS) {
+        const int m = (int)std::min<size_t>(LVN_TABLE_JOBS, todo.size() - first);
+        TableJobs jobs = {};
+        for (int i = 0; i < m; i++) {
+            FieldEntry *fe = todo[first + i];
+            draw_cuckoo_params(fe->params);
+            TableJob &j = jobs.job[i];
+            j.keys = (const unsigned int *)fe->d_keys;
+            j.table = fe->d_table;
+            j.failed = d_flags + first + i;
+            j.count = (unsigned int)fe->numEdges;
+            j.prime = fe->prime;
+            memcpy(j.p, fe->params, sizeof(j.p));
+            fe->cuckooRetries = attempt;
+        }
+        launch_table_builds(jobs, m, st);
         ctx->stats.launches[LVN_STAGE_CUCKOO] += 2;
     }
     return LVN_SUCCESS;
@@ -1606,6 +1618,8 @@ static int apply_csg_items(lvn_meshgen *ctx, const std::vector<CsgItem> &items)
     if (n == 0) return LVN_SUCCESS;
     const Dims &d = ctx->dims;
     cudaStream_t st = ctx->stream;
+    const double t0 = ctx->trace ? host_now_us() : 0.0;   // LVN_TRACE: where an edit's host time goes
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
     std::vector<CsgOpDev> hops;
     std::vector<CsgChunk> hc(n);
     const size_t numWords = ((size_t)3 * d.H * d.H * d.H + 31) / 32;
@@ -1631,29 +1645,40 @@ static int apply_csg_items(lvn_meshgen *ctx, const std::vector<CsgItem> &items)
             hops.push_back(v);
         }
     }
-    LV(ctx->d_ops.reserve(std::max<size_t>(hops.size(), 1)));
-    LV(ctx->d_touched.reserve(numWords * n));
-    LV(ctx->d_csgCounts.reserve((size_t)8 * n));
+    // one pinned staging block [chunks | ops] and one upload; the counters and the touched-edge bitmaps are one
+    // block [8 counters per chunk | ticket | bitmaps] and one memset; the counters come back through the mapped
+    // mirror, written by k_csg_count's last block (no copy-engine hop in front of the host wait)
+    const size_t chunkBytes = ((size_t)n * sizeof(CsgChunk) + 15) & ~(size_t)15;
+    const size_t stageBytes = chunkBytes + std::max<size_t>(hops.size(), 1) * sizeof(CsgOpDev);
+    const size_t countWords = (((size_t)8 * n + 1) + 3) & ~(size_t)3;
+    LV(ctx->h_csgStage.reserve(stageBytes + chunkBytes));   // second part: the chunks as re-sent for the emit pass
+    LV(ctx->d_csgStage.reserve(stageBytes));
+    LV(ctx->d_touched.reserve(countWords + numWords * n));
     LV(ctx->h_small.reserve((size_t)8 * n));
-    LV(ctx->d_csgChunks.reserve(n));
+    unsigned int *h_counts_dev = ctx->h_small.dev();
+    if (!h_counts_dev) { g_lastCudaError = "pinned counter mirror is not mapped"; return LVN_ERR_CUDA; }
+    CsgChunk *d_chunks = (CsgChunk *)ctx->d_csgStage.p;
+    const CsgOpDev *d_ops = (const CsgOpDev *)(ctx->d_csgStage.p + chunkBytes);
+    unsigned int *d_counts = ctx->d_touched.p, *d_ticket = d_counts + (size_t)8 * n, *d_bitmaps = d_counts + countWords;
     for (int i = 0; i < n; i++) {
         FieldEntry &fe = *items[i].fe;
         CsgChunk &c = hc[i];
         c.field = fe.d_field;
-        c.touched = ctx->d_touched.p + numWords * i;
+        c.touched = d_bitmaps + numWords * i;
         c.oldKeys = fe.d_keys; c.oldInfo = fe.d_info; c.numOld = fe.numEdges;
-        c.counts = ctx->d_csgCounts.p + 8 * i;
+        c.counts = d_counts + 8 * i;
     }
-    CU(cudaMemcpyAsync(ctx->d_ops.p, hops.data(), hops.size() * sizeof(CsgOpDev), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_csgChunks.p, hc.data(), n * sizeof(CsgChunk), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(ctx->d_touched.p, 0, numWords * n * sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(ctx->d_csgCounts.p, 0, (size_t)8 * n * sizeof(unsigned int), st));
+    memcpy(ctx->h_csgStage.p, hc.data(), (size_t)n * sizeof(CsgChunk));
+    memcpy(ctx->h_csgStage.p + chunkBytes, hops.data(), hops.size() * sizeof(CsgOpDev));
+    CU(cudaMemcpyAsync(ctx->d_csgStage.p, ctx->h_csgStage.p, stageBytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_counts, 0, (countWords + numWords * n) * sizeof(unsigned int), st));
     {
         StageTimer t(ctx, LVN_STAGE_CSG, 2);
-        launch_csg_materials_count(d, ctx->d_csgChunks.p, n, ctx->d_ops.p, st);
+        launch_csg_materials_count(d, d_chunks, n, d_ops, d_ticket, h_counts_dev, st);
     }
-    CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_csgCounts.p, (size_t)8 * n * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));   // also: hops / hc must outlive their uploads
+    if (ctx->trace) t1 = host_now_us();
+    CU(cudaStreamSynchronize(st));
+    if (ctx->trace) t2 = host_now_us();
     collect_stage_times(ctx);
 
     // When every old edge is invalidated the reference keeps the stale list (numPrunedEdges == 0
@@ -1674,9 +1699,11 @@ static int apply_csg_items(lvn_meshgen *ctx, const std::vector<CsgItem> &items)
         }
     }
     if (anyEmit) {
-        CU(cudaMemcpyAsync(ctx->d_csgChunks.p, hc.data(), n * sizeof(CsgChunk), cudaMemcpyHostToDevice, st));
+        // the staging block's second part: rewritten by the next edit only behind that edit's own host wait
+        memcpy(ctx->h_csgStage.p + stageBytes, hc.data(), (size_t)n * sizeof(CsgChunk));
+        CU(cudaMemcpyAsync(d_chunks, ctx->h_csgStage.p + stageBytes, (size_t)n * sizeof(CsgChunk), cudaMemcpyHostToDevice, st));
         StageTimer t(ctx, LVN_STAGE_CSG, 1);
-        launch_csg_emit(d, ctx->d_csgChunks.p, n, ctx->d_ops.p, st);
+        launch_csg_emit(d, d_chunks, n, d_ops, st);
     }
     std::vector<FieldEntry *> rebuild;
     for (int i = 0; i < n; i++) {
@@ -1695,9 +1722,14 @@ static int apply_csg_items(lvn_meshgen *ctx, const std::vector<CsgItem> &items)
     }
     // no host wait here: the uploads above came from pageable memory (staged before the call returned), the
     // tables' insert flags are read behind the next synchronisation of the stream (validate_pending_tables)
+    if (ctx->trace) t3 = host_now_us();
     LV(build_cuckoo_tables(ctx, rebuild, !ctx->profiling));
     if (ctx->profiling) { CU(cudaStreamSynchronize(st)); collect_stage_times(ctx); }
     CU(cudaGetLastError());
+    if (ctx->trace)
+        fprintf(stderr, "[lvn trace] edit of %d chunks: host %.0f us to enqueue materials + count, %.0f us waiting for the counts, "
+                        "%.0f us to size and enqueue emit, %.0f us to enqueue %d hash tables\n",
+                n, t1 - t0, t2 - t1, t3 - t2, host_now_us() - t3, (int)rebuild.size());
     return LVN_SUCCESS;
 }
 

@@ -54,10 +54,18 @@ __device__ __forceinline__ float snoise2(const float2 *__restrict__ grad, float 
     return 70.f * (n0 + n1 + n2);
 }
 
+// the column of a corner's second lookup, one byte per texel behind the 65536 gradients: the first lookup of a
+// corner used to fetch a whole float4 for its w (4 data-pipe wavefronts per warp where the bytes of a row share
+// one: the L1 data pipe was the generic Hermite kernel's busiest unit, 80 %)
+__device__ __forceinline__ const unsigned char *snoise3_columns(const float4 *grad3)
+{
+    return reinterpret_cast<const unsigned char *>(grad3 + 65536);
+}
+
 __device__ __forceinline__ float corner3(const float4 *__restrict__ grad3, int ci, int cj, int ck,
                                          float x, float y, float z)
 {
-    const int col = __float_as_int(__ldg(&grad3[((cj & 255) << 8) | (ci & 255)]).w);
+    const int col = __ldg(&snoise3_columns(grad3)[((cj & 255) << 8) | (ci & 255)]);
     const float4 g = __ldg(&grad3[((ck & 255) << 8) | col]);
     const float r = __fmaf_rn(z, z, __fmaf_rn(y, y, x * x));
     // "0.6 - dot(Pf, Pf)": the unsuffixed 0.6 is a double (simplex.cl:184,196,208,220) -- subtract in
@@ -422,7 +430,7 @@ __device__ __forceinline__ float corner3_tail(const float4 *__restrict__ grad3, 
                                               float &t)
 {
     // returns the gradient dot; t = (float)(0.6 - (double)r), culled corners are handled by the caller
-    const int col = __float_as_int(__ldg(&grad3[((cj & 255) << 8) | (ci & 255)]).w);
+    const int col = __ldg(&snoise3_columns(grad3)[((cj & 255) << 8) | (ci & 255)]);
     const float4 g = __ldg(&grad3[((ck & 255) << 8) | col]);
     t = (float)(0.6 - (double)r);
     return __fmaf_rn(g.z, z, __fmaf_rn(g.y, y, g.x * x));
@@ -453,6 +461,8 @@ __device__ __forceinline__ float2 snoise3x2(const float4 *__restrict__ grad3, fl
     const float2 t = mul2(add2(add2(ix, iy), iz), rep2(LVN_G3), nz);
     const float2 x0 = sub2(px, sub2(ix, t)), y0 = sub2(py, sub2(iy, t)), z0 = sub2(pz, sub2(iz, t));
     // simplex ordering per position (simplex.cl:169-180), as the reference writes it; the offsets are exactly 0 or 1
+    // (twice rewritten in integers -- same truth table, checked by brute force on the host -- and twice the
+    // stress field came out different and the kernel slower: profiles/r02_notes.md 6; this form stays)
     int o1[2][3], o2[2][3];
 #pragma unroll
     for (int k = 0; k < 2; k++) {

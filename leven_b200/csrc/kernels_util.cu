@@ -53,8 +53,12 @@ void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cuda
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int cuckoo_hash(unsigned int key, unsigned int a, unsigned int b, unsigned int prime)
 {
-    const unsigned long long h = (unsigned long long)(unsigned int)(a * key);   // 32-bit wrap, cuckoo.cl:21
-    return (unsigned int)(((h + b) % 4294967291ull) % prime);
+    // 32-bit wrap of the product, cuckoo.cl:21; the sum is below 2^33: the first modulus is at most two
+    // subtractions and leaves a 32-bit value for the second
+    unsigned long long h = (unsigned long long)(unsigned int)(a * key) + b;
+    if (h >= 4294967291ull) h -= 4294967291ull;
+    if (h >= 4294967291ull) h -= 4294967291ull;
+    return (unsigned int)h % prime;
 }
 
 // One thread per key; the eviction chain is 32 atomic exchanges long (CUCKOO_MAX_ITERATIONS).
@@ -92,6 +96,48 @@ void launch_cuckoo_insert(const unsigned int *keys, unsigned int count, unsigned
     if (!count) return;
     k_cuckoo_insert<<<(count + 255) / 256, 256, 0, s>>>(keys, count, table, prime,
                                                        p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], failed);
+}
+
+// The same for many tables in two launches (an edit rebuilds the table of every chunk it touched): the jobs
+// travel by value in the kernel parameters, blockIdx.y selects the job.
+__global__ void k_fill_tables(TableJobs jobs)
+{
+    const TableJob &j = jobs.job[blockIdx.y];
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.prime; i += gridDim.x * blockDim.x) j.table[i] = ~0ull;
+}
+
+__global__ void k_cuckoo_insert_many(TableJobs jobs)
+{
+    const TableJob &j = jobs.job[blockIdx.y];
+    const unsigned int prime = j.prime;
+    for (unsigned int index = blockIdx.x * blockDim.x + threadIdx.x; index < j.count; index += gridDim.x * blockDim.x) {
+        unsigned int key = j.keys[index];
+        unsigned long long entry = ((unsigned long long)index << 32) | key;
+        unsigned int h = cuckoo_hash(key, j.p[0], j.p[1], prime);
+        int i = 0;
+        for (; i < 32; i++) {
+            entry = atomicExch(&j.table[h], entry);
+            if (entry == ~0ull) break;
+            key = (unsigned int)(entry & 0xffffffffull);
+            const unsigned int h0 = cuckoo_hash(key, j.p[0], j.p[1], prime), h1 = cuckoo_hash(key, j.p[2], j.p[3], prime),
+                               h2 = cuckoo_hash(key, j.p[4], j.p[5], prime), h3 = cuckoo_hash(key, j.p[6], j.p[7], prime);
+            if (h == h0) h = h1;
+            else if (h == h1) h = h2;
+            else if (h == h2) h = h3;
+            else if (h == h3) h = h0;
+        }
+        if (i == 32) atomicAdd(j.failed, 1u);
+    }
+}
+
+void launch_table_builds(const TableJobs &jobs, int numJobs, cudaStream_t s)
+{
+    if (numJobs <= 0) return;
+    unsigned int maxPrime = 0, maxCount = 0;
+    for (int i = 0; i < numJobs; i++) { maxPrime = max(maxPrime, jobs.job[i].prime); maxCount = max(maxCount, jobs.job[i].count); }
+    if (!maxPrime) return;
+    k_fill_tables<<<dim3(min((maxPrime + 255u) / 256u, 296u), numJobs), 256, 0, s>>>(jobs);
+    if (maxCount) k_cuckoo_insert_many<<<dim3(min((maxCount + 255u) / 256u, 296u), numJobs), 256, 0, s>>>(jobs);
 }
 
 __global__ void k_cuckoo_find(const unsigned int *__restrict__ keys, unsigned int count,

@@ -99,7 +99,7 @@ struct ChunkScratch {
 struct DensityParams {
     const float2 *grad2;      // [257*257] snoise2 gradients (texel.xy * 4 - 1), wrap-padded
     const float *grad2x;      // [2][257*257] the same table as separate x and y planes (density.cuh: GradTables)
-    const float4 *grad3;      // [256*256] snoise3 gradients xyz, w = bits of the perm column
+    const float4 *grad3;      // [256*256] snoise3 gradients xyz, w = bits of the perm column; then 65536 bytes: the columns alone
     int kind;                 // 0 terrain, 1 stress
     float param;              // stress threshold
     int defaultMaterial;
@@ -165,7 +165,9 @@ struct CsgChunk {
     int opFirst, numOps;          // this chunk's slice of the op array
     int skip;                     // emit pass: nothing changed in this chunk
 };
-void launch_csg_materials_count(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, cudaStream_t s);
+// ticket: one zeroed word; hostCounts: device address of the mapped mirror that receives the 8 counters of every chunk
+void launch_csg_materials_count(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, unsigned int *ticket,
+                                unsigned int *hostCounts, cudaStream_t s);
 void launch_csg_emit(const Dims &d, const CsgChunk *chunks, int n, const CsgOpDev *ops, cudaStream_t s);
 
 // ---- launchers (kernels_util.cu) -------------------------------------------
@@ -173,6 +175,17 @@ int  host_find_next_prime(int n);
 void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t s);
 void launch_cuckoo_insert(const unsigned int *keys, unsigned int count, unsigned long long *table,
                           unsigned int prime, const unsigned int *params8, unsigned int *failed, cudaStream_t s);
+// Cuckoo_InitialiseTable + Cuckoo_InsertKeys of up to LVN_TABLE_JOBS tables in two launches (kernels_util.cu)
+struct TableJob {
+    const unsigned int *keys;
+    unsigned long long *table;
+    unsigned int *failed;          // += 1 per key whose eviction chain did not end
+    unsigned int count, prime;
+    unsigned int p[8];             // a0 b0 a1 b1 a2 b2 a3 b3
+};
+constexpr int LVN_TABLE_JOBS = 32;
+struct TableJobs { TableJob job[LVN_TABLE_JOBS]; };
+void launch_table_builds(const TableJobs &jobs, int numJobs, cudaStream_t s);
 void launch_cuckoo_find(const unsigned int *keys, unsigned int count, const unsigned long long *table,
                         unsigned int prime, const unsigned int *params8, unsigned int *values, cudaStream_t s);
 // device-wide exclusive scan of ints; total written to *total (device)

@@ -43,13 +43,14 @@ def stress_chunks():
     return np.array([[cx * SIZE, cy * SIZE, cz * SIZE, SIZE] for cy in range(4) for cz in range(4) for cx in range(4)], np.int32)
 
 
-def csg_script(num_ops=CSG_OPS):
+def csg_script(num_ops=CSG_OPS, seed=12345):
     """configs[2]: the fixed edit script.  One op per step, alternating cube / sphere, two adds
-    (materials 1-3) then two subtracts, centres from MT19937(12345) within +-2 chunks of the surface
+    (materials 1-3) then two subtracts, centres from MT19937(seed) within +-2 chunks of the surface
     point above the origin, half-dimensions 1-31 voxels (the viewer's brush range 8-248 world units,
     viewer.h:51-52).  Returns tuples (type, shape, material, origin[3], dimensions[3], rotateY) --
-    the argument order of CSGOperationInfo.make."""
-    rng = np.random.RandomState(12345)
+    the argument order of CSGOperationInfo.make.  Another seed gives another script of the same kind (bench.py warms
+    the context with one before it times the fixed script)."""
+    rng = np.random.RandomState(seed)
     sy = CY0 * 64
     ops = []
     for step in range(num_ops):
