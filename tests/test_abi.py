@@ -155,10 +155,11 @@ def test_packed_fp32_is_not_contracted(built):
                     per_fn[cur][op] += 1
     herm = [v for k, v in per_fn.items() if "k_hermite_terrain" in k]
     cols = [v for k, v in per_fn.items() if "k_columns" in k]
-    assert len(herm) == 1 and len(cols) == 1
+    assert len(herm) == 2 and len(cols) == 1   # the run-time-geometry instance and the V = 64 one
     assert cols[0]["FFMA2"] == 301 and cols[0]["FADD2"] == 360, cols[0]
     # two inlined evaluations (phase A, phase B)
-    assert herm[0]["FFMA2"] >= 2 * 301 and herm[0]["FADD2"] == 2 * 360, herm[0]
+    for h in herm:
+        assert h["FFMA2"] >= 2 * 301 and h["FADD2"] == 2 * 360, h
     # the split kernels: one evaluation each
     for name in ("k_hermite_search", "k_hermite_normals"):
         ks = [v for k, v in per_fn.items() if name in k]
