@@ -472,6 +472,7 @@ struct lvn_meshgen {
     DevBuf<int> d_candidates;      // per lane slice: the chunks that can contain surface (k_candidates -> k_rows)
     DevBuf<TileRef> d_edgeTiles, d_nodeTiles;  // tile directories, one slice per lane
     DevBuf<uint8_t> d_tmpFields;
+    DevBuf<float> d_tmpDensity;   // the density values behind d_tmpFields (ChunkDesc::latticeDensity)
     DevBuf<uint8_t *> d_fieldPtrs;
     // debug stage outputs
     DevBuf<unsigned int> d_dbgCodes;
@@ -595,7 +596,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_rowQ.release(); ctx->d_rowS.release(); ctx->d_edgeKeys.release(); ctx->d_edgeInfo.release(); ctx->d_xzList.release();
     ctx->d_vertices.release(); ctx->d_qef.release(); ctx->d_tris.release(); ctx->d_seams.release();
     ctx->d_slab.release(); ctx->d_slabEy.release(); ctx->d_ticket.release(); ctx->d_candidates.release();
-    ctx->d_tmpFields.release(); ctx->d_fieldPtrs.release();
+    ctx->d_tmpFields.release(); ctx->d_tmpDensity.release(); ctx->d_fieldPtrs.release();
     ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
@@ -933,8 +934,11 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
     }
     if (numTmpFields) {
         LV(ctx->d_tmpFields.reserve((size_t)numTmpFields * F3));
-        for (int k = 0; k < numTmpFields; k++)
+        LV(ctx->d_tmpDensity.reserve((size_t)numTmpFields * F3));
+        for (int k = 0; k < numTmpFields; k++) {
             ctx->h_descs.p[tmpFieldChunk[k]].field = ctx->d_tmpFields.p + (size_t)k * F3;
+            ctx->h_descs.p[tmpFieldChunk[k]].latticeDensity = ctx->d_tmpDensity.p + (size_t)k * F3;
+        }
     }
     // first-guess arena sizes; a batch that needs more reports it in the counters and is re-run
     LV(ctx->d_edgeKeys.reserve(std::max<size_t>((size_t)n * 2048, 1u << 16)));

@@ -20,6 +20,8 @@ struct ChunkDesc {
     int edgeMode;          // EDGES_*
     int cachedNumEdges;    // EDGES_CACHED
     const uint8_t *field;  // SRC_FIELD: u8 materials, F^3
+    const float *latticeDensity;     // a 3-D density field made in this batch: its F^3 density values (k_field_density),
+                                     // i.e. steps 0 and 16 of every edge's zero-crossing search; else null
     const int *cachedKeys;           // EDGES_CACHED: the field's edge list (arbitrary order)
     const float4 *cachedInfo;
     const unsigned long long *cuckooTable;   // edge key -> slot in cachedKeys (a9)
