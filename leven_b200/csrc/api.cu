@@ -934,10 +934,12 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
     }
     if (numTmpFields) {
         LV(ctx->d_tmpFields.reserve((size_t)numTmpFields * F3));
-        LV(ctx->d_tmpDensity.reserve((size_t)numTmpFields * F3));
+        // the density values behind the materials, for k_hermite (4 F^3 bytes per chunk: up to 8 GB of them)
+        const bool keepDensity = (size_t)numTmpFields * F3 * sizeof(float) <= ((size_t)8 << 30);
+        if (keepDensity) LV(ctx->d_tmpDensity.reserve((size_t)numTmpFields * F3));
         for (int k = 0; k < numTmpFields; k++) {
             ctx->h_descs.p[tmpFieldChunk[k]].field = ctx->d_tmpFields.p + (size_t)k * F3;
-            ctx->h_descs.p[tmpFieldChunk[k]].latticeDensity = ctx->d_tmpDensity.p + (size_t)k * F3;
+            ctx->h_descs.p[tmpFieldChunk[k]].latticeDensity = keepDensity ? ctx->d_tmpDensity.p + (size_t)k * F3 : nullptr;
         }
     }
     // first-guess arena sizes; a batch that needs more reports it in the counters and is re-run
