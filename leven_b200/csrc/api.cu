@@ -487,7 +487,6 @@ struct lvn_meshgen {
     // h_tableFlags behind the stream's next synchronisation, run_batch looks at them before it trusts
     // a result that read those tables (validate_pending_tables)
     std::vector<FieldEntry *> pendingTables;
-    DevBuf<unsigned int> d_tableFlags;
     PinBuf<unsigned int> h_tableFlags;
     int lookahead = 2;                     // host path: lanes queued ahead of the one whose copies are being queued (LVN_LOOKAHEAD)
     bool forceTableRetry = false;          // LVN_TEST_CUCKOO_RETRY=1: treat every first insertion as failed (tests)
@@ -600,7 +599,7 @@ extern "C" void lvn_meshgen_destroy(lvn_meshgen *ctx)
     ctx->d_edgeTiles.release(); ctx->d_nodeTiles.release();
     ctx->d_dbgCodes.release(); ctx->d_dbgMasks.release(); ctx->d_dbgMats.release(); ctx->d_dbgQefs.release();
     ctx->d_dbgPos.release(); ctx->d_dbgNrm.release(); ctx->d_touched.release(); ctx->d_csgCounts.release();
-    ctx->d_csgStage.release(); ctx->h_csgStage.release(); ctx->d_tableFlags.release(); ctx->h_tableFlags.release();
+    ctx->d_csgStage.release(); ctx->h_csgStage.release(); ctx->h_tableFlags.release();
     ctx->d_simpRes.release(); ctx->d_packOff.release(); ctx->d_packV.release(); ctx->d_packP.release(); ctx->d_packT.release();
     ctx->h_simpRes.release(); ctx->h_packOff.release();
     if (ctx->simpStreamB) cudaStreamDestroy(ctx->simpStreamB);
@@ -1472,10 +1471,11 @@ static int validate_pending_tables(lvn_meshgen *ctx, bool *rebuilt);
 
 // queue Cuckoo_InitialiseTable + Cuckoo_InsertKeys with fresh parameters for every entry of the list; flag i
 // (device) becomes non-zero when a key of entry i could not be placed
-static int enqueue_table_builds(lvn_meshgen *ctx, const std::vector<FieldEntry *> &todo, unsigned int *d_flags, int attempt)
+static int enqueue_table_builds(lvn_meshgen *ctx, const std::vector<FieldEntry *> &todo, unsigned int *d_flags, int attempt,
+                                bool flagsClearedByHost = false)
 {
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(d_flags, 0, todo.size() * sizeof(unsigned int), st));
+    if (!flagsClearedByHost) CU(cudaMemsetAsync(d_flags, 0, todo.size() * sizeof(unsigned int), st));
     for (size_t first = 0; first < todo.size(); first += LVN_TABLE_JOBS) {
         const int m = (int)std::min<size_t>(LVN_TABLE_JOBS, todo.size() - first);
         TableJobs jobs = {};
@@ -1540,10 +1540,13 @@ static int build_cuckoo_tables(lvn_meshgen *ctx, const std::vector<FieldEntry *>
     if (todo.empty()) return LVN_SUCCESS;
     StageTimer t(ctx, LVN_STAGE_CUCKOO, 0);
     if (!defer) return retry_table_builds(ctx, todo, 0);
-    LV(ctx->d_tableFlags.reserve(todo.size()));
+    // the flags of a deferred build live in the mapped pinned mirror itself: cleared here (nothing is pending, see
+    // above), set by the insert kernel in the rare failure: no memset and no copy on the stream
     LV(ctx->h_tableFlags.reserve(todo.size()));
-    LV(enqueue_table_builds(ctx, todo, ctx->d_tableFlags.p, 0));
-    CU(cudaMemcpyAsync(ctx->h_tableFlags.p, ctx->d_tableFlags.p, todo.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    unsigned int *flagsDev = ctx->h_tableFlags.dev();
+    if (!flagsDev) { g_lastCudaError = "pinned flag mirror is not mapped"; return LVN_ERR_CUDA; }
+    memset(ctx->h_tableFlags.p, 0, todo.size() * sizeof(unsigned int));
+    LV(enqueue_table_builds(ctx, todo, flagsDev, 0, true));
     ctx->pendingTables = todo;
     return LVN_SUCCESS;
 }

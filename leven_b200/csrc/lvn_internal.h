@@ -181,7 +181,7 @@ void launch_cuckoo_insert(const unsigned int *keys, unsigned int count, unsigned
 struct TableJob {
     const unsigned int *keys;
     unsigned long long *table;
-    unsigned int *failed;          // += 1 per key whose eviction chain did not end
+    unsigned int *failed;          // set to 1 when the eviction chain of a key did not end (device or mapped host memory)
     unsigned int count, prime;
     unsigned int p[8];             // a0 b0 a1 b1 a2 b2 a3 b3
 };
