@@ -490,6 +490,7 @@ struct lvn_meshgen {
     PinBuf<unsigned int> h_tableFlags;
     int lookahead = 2;                     // host path: lanes queued ahead of the one whose copies are being queued (LVN_LOOKAHEAD)
     bool forceTableRetry = false;          // LVN_TEST_CUCKOO_RETRY=1: treat every first insertion as failed (tests)
+    bool noLatticeDensity = false;         // LVN_TEST_NO_LATTICE_DENSITY=1: k_hermite evaluates all 17 steps itself (tests)
     // simplified batch (lvn_meshgen_generate_simplified_batch)
     DevBuf<int4> d_simpRes;
     DevBuf<int2> d_packOff;
@@ -579,6 +580,7 @@ extern "C" lvn_meshgen *lvn_meshgen_create(int voxelsPerChunk)
     if (const char *e = getenv("LVN_STREAMS")) ctx->cfgStreams = atoi(e);
     if (const char *e = getenv("LVN_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char *e = getenv("LVN_TEST_CUCKOO_RETRY")) ctx->forceTableRetry = atoi(e) != 0;
+    if (const char *e = getenv("LVN_TEST_NO_LATTICE_DENSITY")) ctx->noLatticeDensity = atoi(e) != 0;
     if (const char *e = getenv("LVN_LOOKAHEAD")) ctx->lookahead = std::max(1, atoi(e));
     return ctx;
 }
@@ -934,7 +936,7 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
     if (numTmpFields) {
         LV(ctx->d_tmpFields.reserve((size_t)numTmpFields * F3));
         // the density values behind the materials, for k_hermite (4 F^3 bytes per chunk: up to 8 GB of them)
-        const bool keepDensity = (size_t)numTmpFields * F3 * sizeof(float) <= ((size_t)8 << 30);
+        const bool keepDensity = !ctx->noLatticeDensity && (size_t)numTmpFields * F3 * sizeof(float) <= ((size_t)8 << 30);
         if (keepDensity) LV(ctx->d_tmpDensity.reserve((size_t)numTmpFields * F3));
         for (int k = 0; k < numTmpFields; k++) {
             ctx->h_descs.p[tmpFieldChunk[k]].field = ctx->d_tmpFields.p + (size_t)k * F3;

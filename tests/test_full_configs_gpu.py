@@ -105,6 +105,39 @@ def test_config4_stress_all_64_chunks(lc, oracle_mod):
         lc.Compute_SetDensityFunction(0, 0.5)
 
 
+def test_stress_hermite_with_and_without_lattice_densities(lc, monkeypatch):
+    """the generic Hermite kernel takes steps 0 and 16 of an edge's search from the density values the field
+    kernel of the same batch left behind; without them (batches beyond 8 GB of such values) it evaluates all 17
+    steps itself: the same meshes, byte for byte"""
+    try:
+        lc.Compute_SetDensityFunction(1, W.STRESS_THRESHOLD)
+        ms = W.stress_chunks()[:8]
+        out = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("LVN_TEST_NO_LATTICE_DENSITY", flag)      # read when the context is created
+            ctx = lc.Compute_MeshGenContext.create(64)
+            rc, res, view = ctx.generateBatchDevice(ms)
+            assert rc == 0
+            V = np.zeros(int(view.totalVertices) + 16, lc.MeshVertex); T = np.zeros(int(view.totalTriangles) + 16, lc.MeshTriangle)
+            S = np.zeros(int(view.totalSeamNodes) + 16, lc.SeamNodeInfo)
+            rc, r = ctx.generateBatch(ms, V, T, S)
+            assert rc == 0
+            out.append((r.copy(), V.copy(), T.copy(), S.copy()))
+            ctx.destroy()
+        (ra, Va, Ta, Sa), (rb, Vb, Tb, Sb) = out
+        assert ra["numVertices"].sum() > 100000
+        for k in ("numEdges", "numVertices", "numTriangles", "numSeamNodes"):
+            assert (ra[k] == rb[k]).all(), k
+        for i in range(len(ms)):
+            for arr_a, arr_b, off, cnt in ((Va, Vb, "vertexOffset", "numVertices"), (Ta, Tb, "triangleOffset", "numTriangles"),
+                                           (Sa, Sb, "seamOffset", "numSeamNodes")):
+                a = arr_a[ra[off][i]:ra[off][i] + ra[cnt][i]]
+                b = arr_b[rb[off][i]:rb[off][i] + rb[cnt][i]]
+                assert a.tobytes() == b.tobytes(), (i, cnt)
+    finally:
+        lc.Compute_SetDensityFunction(0, 0.5)
+
+
 def test_config3_csg_script_on_ring(lc, oracle_mod, ctx, gpu_world):
     """the 32-op script, one op per step on the ring's fields; after each op the touched chunks are
     compared stage by stage and re-meshed through the batch call config 3 times"""
