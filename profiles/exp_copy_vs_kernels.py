@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Does a bulk device->host copy in flight slow the chunk kernels down?  The device-resident ring batch, timed
-alone and while a second stream copies 34 MB blocks to pinned memory back to back."""
+"""Does a bulk copy in flight slow the chunk kernels down?  The device-resident ring batch, timed alone and while
+a second stream copies 34 MB blocks back to back: device -> pinned host, pinned host -> device, device -> device."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -27,9 +27,13 @@ for lanes in ((2, 2), (1, 1), (8, 2)):
         torch.cuda.synchronize()
         return float(np.median([a.elapsed_time(b) for a, b in evs]))
     alone = run(30)
-    with torch.cuda.stream(side):
-        for _ in range(400):
-            dst.copy_(src, non_blocking=True)        # ~0.6 ms each: ~240 ms of continuous D2H
-    under = run(30)
-    torch.cuda.synchronize()
-    print(f"lanes x streams {lanes}: batch alone {alone:.3f} ms, with a D2H copy in flight {under:.3f} ms")
+    src2 = torch.empty(34 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    for kind, a, b, reps in (("D2H", dst, src, 400), ("H2D", src, dst, 400), ("D2D", src2, src, 4000)):
+        with torch.cuda.stream(side):
+            for _ in range(reps):
+                a.copy_(b, non_blocking=True)        # ~0.6 ms each over PCIe: ~240 ms of continuous copying
+        res[kind] = run(30)
+        torch.cuda.synchronize()
+    print(f"lanes x streams {lanes}: batch alone {alone:.3f} ms; with a copy in flight: " +
+          ", ".join(f"{k} {v:.3f} ms" for k, v in res.items()))
