@@ -712,7 +712,8 @@ def bench_csg(lc, ctx, torch, stream, flush, fp32_peak, hbm_peak):
     # bitmap (3 H^3 bits, set + read); its flops: K ops x F^3 x C_brush (25 sphere / 45 box)
     csg_bytes = edits * (2 * F3 + 2 * 3 * (V + 1) ** 3 / 8)
     return {"workload": "configs[2]: 32 scripted sphere/cube add/subtract ops on the 512-chunk ring's fields, one op per step; "
-                        "re-mesh only the chunks whose AABB overlaps the op's bounds",
+                        "re-mesh only the chunks whose AABB overlaps the op's bounds; every timed op is a first application "
+                        "(a real edit) on a context warmed by another script of the same kind",
             "ops": len(apply_ms), "chunk_edits": edits,
             "e2e_ms_per_op": spread(np.asarray(apply_ms) + np.asarray(mesh_ms)), "wall_ms_per_op": spread(wall_ms),
             "apply_ms_per_op": spread(apply_ms), "remesh_ms_per_op": spread(mesh_ms),
