@@ -518,12 +518,20 @@ def main():
         gather = sharding.CountGather(len(sweep), rank, world_size, device=dev if world_size > 1 else None)
 
         def sweep_device():
-            res = sw.step_device()
+            # the counts are final after the classify kernels: the call returns with them while the Hermite / leaves /
+            # solve kernels run, and the gather (on its own stream) crosses NVLink under them
+            rc, res, _ = ctx.generateBatchDeviceAsync(sw.ms)
+            assert rc == 0
             gather.gather(res["numVertices"], res["numTriangles"], res["numSeamNodes"])
+            assert ctx.wait() == 0
 
         def sweep_e2e():
-            res = sw.step_e2e()
+            # likewise: the call returns when every lane's counts are in and its copies are queued; the gather runs
+            # while the last lanes compute and cross PCIe
+            rc, res = ctx.generateBatchAsync(sw.ms, sw.hostV, sw.hostT, sw.hostS)
+            assert rc == 0
             gather.gather(res["numVertices"], res["numTriangles"], res["numSeamNodes"])
+            assert ctx.wait() == 0
 
         n_dev = batches_for(sweep_device, args.steps, 3) * args.steps
         sd_ms, _ = timed_batches(sweep_device, n_dev)

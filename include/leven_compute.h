@@ -161,6 +161,25 @@ typedef struct lvn_batch_device_view {
 int lvn_meshgen_generate_batch_device(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
                                       lvn_chunk_result *results, lvn_batch_device_view *view);
 
+/* The same, returning as soon as every chunk's counts and arena offsets are final (after the classify kernels of
+ * every lane) with the rest of the batch queued on the context's stream: `results` and the view's totals are
+ * valid on return, the arenas in stream order on that stream or after lvn_meshgen_wait.  For callers that can
+ * use the counts while the meshes are still being made: the count gather of a sharded sweep, the
+ * sizing of a consumer's buffers.  A batch that has to grow its arenas or rebuild a hash table completes before
+ * the call returns, like lvn_meshgen_generate_batch_device. */
+int lvn_meshgen_generate_batch_device_async(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                            lvn_chunk_result *results, lvn_batch_device_view *view);
+/* blocks until everything queued on the context's stream has run */
+int lvn_meshgen_wait(lvn_meshgen *ctx);
+/* lvn_meshgen_generate_batch the same way: returns once every lane's counts are published and its copies are
+ * queued; `results` are final on return, the host arenas complete after lvn_meshgen_wait (the caller must not
+ * free or reuse them before) */
+int lvn_meshgen_generate_batch_async(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                     lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                     lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                     lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                     lvn_chunk_result *results);
+
 /* applyCSGOperations over many chunks in one pass (same ops for every chunk) */
 int lvn_meshgen_apply_csg_operations_batch(lvn_meshgen *ctx, const lvn_csg_operation_info *ops, int numOps,
                                            int nChunks, const int32_t *chunkMinSize);

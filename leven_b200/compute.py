@@ -110,6 +110,9 @@ ABI = {
     "lvn_meshgen_generate_chunk_mesh": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _P]),
     "lvn_meshgen_generate_batch": (_I, [_P, _I, _P, _P, _I64, _P, _I64, _P, _I64, _P]),
     "lvn_meshgen_generate_batch_device": (_I, [_P, _I, _P, _P, _P]),
+    "lvn_meshgen_generate_batch_device_async": (_I, [_P, _I, _P, _P, _P]),
+    "lvn_meshgen_wait": (_I, [_P]),
+    "lvn_meshgen_generate_batch_async": (_I, [_P, _I, _P, _P, _I64, _P, _I64, _P, _I64, _P]),
     "lvn_meshgen_apply_csg_operations_batch": (_I, [_P, _P, _I, _I, _P]),
     "lvn_meshgen_debug_dump_chunk": (_I, [_P, _P, _I, _P]),
     "lvn_debug_solve_qefs": (_I, [_I, _I, _P, _P]),
@@ -334,6 +337,29 @@ class Compute_MeshGenContext:
         rc = self._L.lvn_meshgen_generate_batch_device(self.privateCtx_, len(ms), _ptr(ms), _ptr(results),
                                                        C.byref(view))
         return rc, results, view
+
+    def generateBatchDeviceAsync(self, chunkMinSize):
+        """generateBatchDevice that returns once the counts and offsets are final; the arenas are complete in
+        stream order on the context's stream, or after wait().  Returns (error, results, view)"""
+        ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
+        results = np.zeros(len(ms), ChunkResult)
+        view = BatchDeviceView()
+        rc = self._L.lvn_meshgen_generate_batch_device_async(self.privateCtx_, len(ms), _ptr(ms), _ptr(results),
+                                                             C.byref(view))
+        return rc, results, view
+
+    def wait(self):
+        return self._L.lvn_meshgen_wait(self.privateCtx_)
+
+    def generateBatchAsync(self, chunkMinSize, vertices, triangles, seamNodes):
+        """generateBatch that returns once the counts are final and every copy is queued; the host arenas are
+        complete after wait().  Returns (error, results)"""
+        ms = np.ascontiguousarray(chunkMinSize, np.int32).reshape(-1, 4)
+        results = np.zeros(len(ms), ChunkResult)
+        rc = self._L.lvn_meshgen_generate_batch_async(self.privateCtx_, len(ms), _ptr(ms),
+                                                      _ptr(vertices), len(vertices), _ptr(triangles), len(triangles),
+                                                      _ptr(seamNodes), len(seamNodes), _ptr(results))
+        return rc, results
 
     def generateSimplifiedBatch(self, chunkMinSize, vertices, triangles, seamNodes, unitOptions=None):
         """ConstructClipmapNodeData (clipmap.cpp:432-468) over a batch: generateChunkMesh + ngMeshSimplifier,

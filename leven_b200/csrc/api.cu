@@ -750,6 +750,8 @@ struct BatchOpts {
     bool debug = false;          // fill the per-node stage dumps
     bool ignoreFieldCache = false;
     bool singleLane = false;     // keep descriptors / headers in the caller's order
+    bool countsFirst = false;    // device path: return once every lane's counts are published (they are final after
+                                 // k_rows); the arenas are complete in stream order on the context's stream
 };
 
 struct HostOut {   // caller-owned destination of lvn_meshgen_generate_batch
@@ -808,7 +810,7 @@ static void choose_pipeline(const lvn_meshgen *ctx, int n, const BatchOpts &opts
 static double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // every stream a lane ran on, and the copy stream, rejoin the context's stream
-static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies)
+static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies, bool hostSync = true)
 {
     for (int r = 1; r < numStreams; r++) {
         CU(cudaEventRecord(ctx->evJoin[r], ctx->laneStreams[r]));
@@ -820,7 +822,7 @@ static int join_lanes(lvn_meshgen *ctx, int numStreams, bool copies)
         CU(cudaEventRecord(ctx->evPubJoin, ctx->pubStream));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->evPubJoin, 0));
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (hostSync) CU(cudaStreamSynchronize(ctx->stream));
     return LVN_SUCCESS;
 }
 
@@ -1009,6 +1011,8 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
     auto lane_counters_dev = [&](int k) { return (ArenaCounters *)(ctx->d_hdrs.p + ctx->laneFirst[k + 1] + k); };
     auto lane_counters_host = [&](int k) { return (const ArenaCounters *)(ctx->h_hdrs.p + ctx->laneFirst[k + 1] + k); };
 
+    // counts first (device path): nothing that needs the whole batch on the host may be pending
+    const bool countsFirst = opts.countsFirst && !opts.debug && !ctx->profiling && !ctx->trace && ctx->pendingTables.empty();
     for (int attempt = 0; attempt < 3; attempt++) {
         if (opts.debug) {
             LV(ctx->d_dbgCodes.reserve(ctx->d_vertices.cap)); LV(ctx->d_dbgMasks.reserve(ctx->d_vertices.cap));
@@ -1058,7 +1062,7 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
             // are published right away from a side stream, so that the host can size and queue the
             // lane's copies (behind evLane) long before the lane's last kernel ends: the copy engine
             // then starts the moment the lane is done, with no host round trip in between.
-            const bool earlyPublish = out != nullptr;
+            const bool earlyPublish = out != nullptr || countsFirst;   // (the host path always publishes early)
             if (earlyPublish) {
                 CU(cudaEventRecord(ctx->evRows[k], ls));
                 CU(cudaStreamWaitEvent(ctx->pubStream, ctx->evRows[k], 0));
@@ -1102,8 +1106,18 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
         };
 
         bool overflow = false, hostFull = false;
+        bool joinInStreamOrder = false;
         if (!out) {
             for (int k = 0; k < S; k++) LV(enqueue_lane(k));
+            if (countsFirst) {
+                // every lane's headers and counters are in the mirror once its k_publish has run; without an
+                // overflow nothing else of the batch is needed on the host
+                joinInStreamOrder = true;
+                for (int k = 0; k < S; k++) {
+                    CU(cudaEventSynchronize(ctx->evPub[k]));
+                    if (lane_counters_host(k)->overflow) joinInStreamOrder = false;
+                }
+            }
         } else {
             // host path: keep two lanes queued ahead of the one being drained over the copy
             // engine, so that neither the SMs nor the PCIe link wait for the host
@@ -1149,10 +1163,12 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
                     cudaEventRecord(ctx->traceCopyEv[k], cs);
                 }
             }
+            // every lane's counts are in and its copies are queued: a counts-first caller gets them now
+            joinInStreamOrder = countsFirst && !overflow && !hostFull;
         }
 #undef LVN_TRACE_EV
         const double j0 = ctx->trace ? host_now_us() : 0.0;
-        LV(join_lanes(ctx, R, out != nullptr));
+        LV(join_lanes(ctx, R, out != nullptr || countsFirst, !joinInStreamOrder));
         if (ctx->trace) {
             hostWaited += host_now_us() - j0;
             fprintf(stderr, "[lvn trace] host thread: %.0f us in the call, %.0f us of them waiting for the GPU (the rest: building the batch, driver calls); "
@@ -1279,6 +1295,53 @@ extern "C" int lvn_meshgen_generate_batch_device(lvn_meshgen *ctx, int nChunks, 
         view->nonEmptyChunks = (int32_t)ctx->lastCounters.nonEmpty;
     }
     return LVN_SUCCESS;
+}
+
+// The device batch for a caller that has something to do with the counts while the meshes are still being made
+// (the count gather of a sharded sweep, sizing a consumer's buffers): returns once every chunk's counts and
+// arena offsets are final -- they are after the classify kernels -- with the rest of the batch queued on the
+// context's stream.  The arenas are complete in stream order on that stream, or after lvn_meshgen_wait.
+extern "C" int lvn_meshgen_generate_batch_device_async(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                                       lvn_chunk_result *results, lvn_batch_device_view *view)
+{
+    BatchOpts opts;
+    opts.countsFirst = true;
+    LV(replay_stored_ops(ctx, nChunks, chunkMinSize));
+    LV(run_batch(ctx, nChunks, chunkMinSize, opts));
+    if (results) fill_results(ctx, nChunks, results);
+    if (view) {
+        view->vertices = ctx->d_vertices.p;
+        view->triangles = (const lvn_mesh_triangle *)ctx->d_tris.p;
+        view->seamNodes = ctx->d_seams.p;
+        view->totalVertices = ctx->lastCounters.nodes;
+        view->totalTriangles = 2 * (int64_t)ctx->lastCounters.quads;
+        view->totalSeamNodes = ctx->lastCounters.seams;
+        view->totalEdges = ctx->lastCounters.edges;
+        view->nonEmptyChunks = (int32_t)ctx->lastCounters.nonEmpty;
+    }
+    return LVN_SUCCESS;
+}
+
+extern "C" int lvn_meshgen_wait(lvn_meshgen *ctx) { return lvn::meshgen_wait(ctx); }
+
+// lvn_meshgen_generate_batch for the same kind of caller: returns once every lane's counts are published and its
+// copies are queued; `results` are final, the host arenas are complete after lvn_meshgen_wait.
+extern "C" int lvn_meshgen_generate_batch_async(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,
+                                                lvn_mesh_vertex *vertices, int64_t vertexCapacity,
+                                                lvn_mesh_triangle *triangles, int64_t triangleCapacity,
+                                                lvn_seam_node_info *seamNodes, int64_t seamCapacity,
+                                                lvn_chunk_result *results)
+{
+    if (!results) return LVN_ERR_INVALID_VALUE;
+    BatchOpts opts;
+    opts.countsFirst = true;
+    HostOut out = {vertices, vertexCapacity, triangles, triangleCapacity, seamNodes, seamCapacity};
+    LV(replay_stored_ops(ctx, nChunks, chunkMinSize));
+    const int rc = run_batch(ctx, nChunks, chunkMinSize, opts, &out);
+    if (rc == LVN_SUCCESS || rc == LVN_ERR_CAPACITY) {
+        if (ctx && ctx->numLanes) fill_results(ctx, nChunks, results);
+    }
+    return rc;
 }
 
 extern "C" int lvn_meshgen_generate_batch(lvn_meshgen *ctx, int nChunks, const int32_t *chunkMinSize,

@@ -84,6 +84,9 @@ class CountGather:
         if on_gpu:
             self.d_in = torch.zeros((3, self.per), dtype=torch.int32, device=device)
             self.d_out = torch.zeros((self.world, 3, self.per), dtype=torch.int32, device=device)
+            # the gather has no input on the device: on a stream of its own it does not queue behind the kernels of
+            # the batch whose counts it carries (lvn_meshgen_generate_batch_device_async returns while they run)
+            self.stream = torch.cuda.Stream(device=device)
 
     def gather(self, num_vertices, num_triangles, num_seam_nodes):
         torch = self.torch
@@ -94,10 +97,11 @@ class CountGather:
         if not multi:
             self.a_out[0] = a
         elif self.device is not None:
-            self.d_in.copy_(self.h_in, non_blocking=True)
-            dist.all_gather_into_tensor(self.d_out.view(-1), self.d_in.view(-1), group=self.group)
-            self.h_out.copy_(self.d_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(self.stream):
+                self.d_in.copy_(self.h_in, non_blocking=True)
+                dist.all_gather_into_tensor(self.d_out.view(-1), self.d_in.view(-1), group=self.group)
+                self.h_out.copy_(self.d_out, non_blocking=True)
+            self.stream.synchronize()
         else:
             dist.all_gather_into_tensor(self.h_out.view(-1), self.h_in.view(-1), group=self.group)
         # chunk i = j * world + r sits at [r][k][j]; the transposition and the exclusive scan are one host loop

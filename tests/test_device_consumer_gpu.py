@@ -69,3 +69,89 @@ def test_device_arenas_consumed_in_place(lc):
         assert len(draws) == int((res["numTriangles"] > 0).sum())
     finally:
         ctx.destroy()
+
+
+def test_async_device_batch_counts_first(lc):
+    """lvn_meshgen_generate_batch_device_async returns with the counts and offsets while the meshes are still being
+    made; after lvn_meshgen_wait the arenas hold, chunk by chunk, the bytes of the synchronous call -- also when a
+    consumer's work is queued behind the batch in stream order instead of waiting on the host"""
+    torch = pytest.importorskip("torch")
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        ms = W.ring_chunks()
+        stream = torch.cuda.current_stream()
+        ctx.setStream(stream.cuda_stream)
+
+        def arenas(res, view):
+            ev = int((res["vertexOffset"] + res["numVertices"]).max()); et = int((res["triangleOffset"] + res["numTriangles"]).max())
+            es = int((res["seamOffset"] + res["numSeamNodes"]).max())
+            return (torch.as_tensor(DeviceArray(view.vertices, ev * 48), device="cuda").view(-1, 48),
+                    torch.as_tensor(DeviceArray(view.triangles, et * 12), device="cuda").view(-1, 12),
+                    torch.as_tensor(DeviceArray(view.seamNodes, max(es, 1) * 48), device="cuda").view(-1, 48))
+
+        def per_chunk(res, dv, dt, ds):
+            out = []
+            for r in res:
+                out.append((dv[r["vertexOffset"]:r["vertexOffset"] + r["numVertices"]].cpu().numpy().tobytes() if r["numTriangles"] else b"",
+                            dt[r["triangleOffset"]:r["triangleOffset"] + r["numTriangles"]].cpu().numpy().tobytes(),
+                            ds[r["seamOffset"]:r["seamOffset"] + r["numSeamNodes"]].cpu().numpy().tobytes()))
+            return out
+
+        rc, res0, view0 = ctx.generateBatchDevice(ms)
+        assert rc == 0
+        want = per_chunk(res0, *arenas(res0, view0))
+        for rep in range(3):
+            rc, res, view = ctx.generateBatchDeviceAsync(ms)
+            assert rc == 0
+            for k in ("numEdges", "numVertices", "numTriangles", "numSeamNodes"):
+                assert (res[k] == res0[k]).all(), k
+            assert view.totalVertices == view0.totalVertices and view.totalTriangles == view0.totalTriangles
+            dv, dt, ds = arenas(res, view)
+            if rep == 1:
+                # a consumer in stream order: its copy is queued on the context's stream, no host wait in between
+                snap = dv.clone()
+                assert ctx.wait() == 0
+                assert torch.equal(snap, dv)
+            else:
+                assert ctx.wait() == 0
+            assert per_chunk(res, dv, dt, ds) == want
+        # the next call of any kind is ordered behind an unfinished one
+        rc, res, view = ctx.generateBatchDeviceAsync(ms)
+        assert rc == 0
+        rc, res2, view2 = ctx.generateBatchDevice(ms[:64])
+        assert rc == 0 and (res2["numVertices"] == res0["numVertices"][:64]).all()
+    finally:
+        ctx.destroy()
+
+
+def test_async_host_batch_counts_first(lc):
+    """lvn_meshgen_generate_batch_async: results on return, host arenas after lvn_meshgen_wait, byte for byte what
+    the synchronous call delivers"""
+    torch = pytest.importorskip("torch")
+    ctx = lc.Compute_MeshGenContext.create(64)
+    try:
+        ms = W.ring_chunks()
+        rc, res0, view = ctx.generateBatchDevice(ms)
+        assert rc == 0
+        nV, nT, nS = int(view.totalVertices) + 64, int(view.totalTriangles) + 64, int(view.totalSeamNodes) + 64
+        pin = [torch.zeros(n * sz, dtype=torch.uint8, pin_memory=True) for n, sz in ((nV, 48), (nT, 12), (nS, 48), (nV, 48), (nT, 12), (nS, 48))]
+        V0, T0, S0 = pin[0].numpy().view(lc.MeshVertex), pin[1].numpy().view(lc.MeshTriangle), pin[2].numpy().view(lc.SeamNodeInfo)
+        V1, T1, S1 = pin[3].numpy().view(lc.MeshVertex), pin[4].numpy().view(lc.MeshTriangle), pin[5].numpy().view(lc.SeamNodeInfo)
+        rc, r0 = ctx.generateBatch(ms, V0, T0, S0)
+        assert rc == 0
+        for rep in range(2):
+            rc, r1 = ctx.generateBatchAsync(ms, V1, T1, S1)
+            assert rc == 0
+            for k in ("numEdges", "numVertices", "numTriangles", "numSeamNodes"):
+                assert (r1[k] == r0[k]).all(), k
+            assert ctx.wait() == 0
+            for a, b in zip(r0, r1):
+                assert V0[a["vertexOffset"]:a["vertexOffset"] + a["numVertices"]].tobytes() == V1[b["vertexOffset"]:b["vertexOffset"] + b["numVertices"]].tobytes()
+                assert T0[a["triangleOffset"]:a["triangleOffset"] + a["numTriangles"]].tobytes() == T1[b["triangleOffset"]:b["triangleOffset"] + b["numTriangles"]].tobytes()
+                assert S0[a["seamOffset"]:a["seamOffset"] + a["numSeamNodes"]].tobytes() == S1[b["seamOffset"]:b["seamOffset"] + b["numSeamNodes"]].tobytes()
+            V1[:] = 0; T1[:] = 0; S1[:] = 0
+        # too small an arena is reported like by the synchronous call
+        rc, r2 = ctx.generateBatchAsync(ms, V1[:1000], T1, S1)
+        assert rc == lc.LVN_ERR_CAPACITY and (r2["numVertices"] == r0["numVertices"]).all()
+    finally:
+        ctx.destroy()
