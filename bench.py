@@ -463,6 +463,41 @@ def main():
     pipe_e2e = ctx.getPipeline()
     sampler.mark()
     clocks = sampler.stop()
+
+    # The same end-to-end step as a stream of batches: two contexts, two sets of host arenas, the counts-first
+    # call (lvn_meshgen_generate_batch_async) for batch i while batch i - 1 still crosses PCIe, lvn_meshgen_wait
+    # before a batch's arenas are touched.  Reported beside `e2e` (which stays one synchronous call per batch).
+    pipelined = None
+    try:
+        ctx_b = lc.Compute_MeshGenContext.create(V)
+        keep_b = [pinned(ring.totV + 1024, lc.MeshVertex), pinned(ring.totT + 1024, lc.MeshTriangle), pinned(ring.totS + 1024, lc.SeamNodeInfo)]
+        pair = [(ctx, (ring.hostV, ring.hostT, ring.hostS)), (ctx_b, tuple(k[1] for k in keep_b))]
+        for _ in range(3):
+            assert ctx_b.generateBatch(ring.ms, *pair[1][1])[0] == 0
+
+        def stream_of_batches(count):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(count):
+                c, a = pair[i % 2]
+                assert c.generateBatchAsync(ring.ms, *a)[0] == 0
+                if i:
+                    assert pair[(i - 1) % 2][0].wait() == 0      # batch i - 1 is complete: its arenas may be read
+            assert pair[(count - 1) % 2][0].wait() == 0
+            barrier()
+            return time.perf_counter() - t0
+
+        stream_of_batches(20)
+        n_pipe = max(20, int(0.5 / (float(np.median(e2e_batch_ms)) * 1e-3)))
+        pipe_s = max_over_ranks(stream_of_batches(n_pipe))
+        pipelined = {"value": world_size * nchunks * n_pipe / pipe_s, "unit": "chunks/s", "ms_per_batch": 1e3 * pipe_s / n_pipe,
+                     "batches": n_pipe, "contexts_in_flight": 2, "timed_region_s": pipe_s,
+                     "clock": "host wall clock between two device synchronisations (the batches of two contexts overlap, "
+                              "so there is no per-batch event pair); no L2 flush between batches",
+                     "api": "lvn_meshgen_generate_batch_async + lvn_meshgen_wait, alternating between two contexts"}
+        ctx_b.destroy()
+    except Exception as e:  # noqa: BLE001
+        pipelined = {"error": repr(e)[:200]}
     # the link itself on this box: the step's download as one device -> pinned-host copy (outside the
     # timed regions; boxes of one pool differ here, and the end-to-end step is bound by it)
     link_bytes = ring.totV * 48 + ring.totT * 12 + ring.totS * 48
@@ -608,7 +643,8 @@ def main():
                          "frac_of_batch": link_ms / (e2e_ms_max / (args.steps * inner_e2e)),
                          "what": "the batch's download as ONE device -> pinned host copy, no kernels running, all ranks copying at the same "
                                  "time (rank 0's figure): the PCIe floor of the batch on this box at this number of GPUs"},
-                "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)"},
+                "api": "lvn_meshgen_generate_batch (host chunk list in, pinned host mesh/seam arenas out)",
+                "pipelined": pipelined},
         "per_rank": {"e2e_ms_per_batch": [r[0] for r in per_rank], "device_ms_per_batch": [r[1] for r in per_rank],
                      "link_gbs": [r[2] for r in per_rank], "link_gbs_sustained": [r[3] for r in per_rank],
                      "link_floor_ms_per_batch": [round(link_bytes / (r[3] * 1e6), 4) for r in per_rank],
