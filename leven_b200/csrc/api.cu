@@ -750,8 +750,8 @@ struct BatchOpts {
     bool debug = false;          // fill the per-node stage dumps
     bool ignoreFieldCache = false;
     bool singleLane = false;     // keep descriptors / headers in the caller's order
-    bool countsFirst = false;    // device path: return once every lane's counts are published (they are final after
-                                 // k_rows); the arenas are complete in stream order on the context's stream
+    bool countsFirst = false;    // return once every lane's counts are published (they are final after k_rows) and, on
+                                 // the host path, its copies are queued; the rest completes in stream order
 };
 
 struct HostOut {   // caller-owned destination of lvn_meshgen_generate_batch
@@ -1011,7 +1011,7 @@ static int run_batch_once(lvn_meshgen *ctx, int n, const int32_t *chunkMinSize, 
     auto lane_counters_dev = [&](int k) { return (ArenaCounters *)(ctx->d_hdrs.p + ctx->laneFirst[k + 1] + k); };
     auto lane_counters_host = [&](int k) { return (const ArenaCounters *)(ctx->h_hdrs.p + ctx->laneFirst[k + 1] + k); };
 
-    // counts first (device path): nothing that needs the whole batch on the host may be pending
+    // counts first: nothing that needs the whole batch on the host may be pending
     const bool countsFirst = opts.countsFirst && !opts.debug && !ctx->profiling && !ctx->trace && ctx->pendingTables.empty();
     for (int attempt = 0; attempt < 3; attempt++) {
         if (opts.debug) {
