@@ -153,5 +153,20 @@ def test_async_host_batch_counts_first(lc):
         # too small an arena is reported like by the synchronous call
         rc, r2 = ctx.generateBatchAsync(ms, V1[:1000], T1, S1)
         assert rc == lc.LVN_ERR_CAPACITY and (r2["numVertices"] == r0["numVertices"]).all()
+        # right behind an edit (hash tables of the edited fields still unvalidated) the call completes the batch
+        # before it returns, like the synchronous one: same meshes
+        op = lc.CSGOperationInfo.make(*W.csg_script()[0])
+        lo, hi = lc.CalcCSGOperationBounds(op)
+        touched = W.touched_chunks(ms, lo, hi)
+        assert len(touched) > 0
+        assert ctx.applyCSGOperationsBatch([op], touched) == 0
+        rc, ra = ctx.generateBatchAsync(touched, V1, T1, S1)
+        assert rc == 0 and ctx.wait() == 0
+        rc, rb = ctx.generateBatch(touched, V0, T0, S0)
+        assert rc == 0 and ra["numVertices"].sum() > 0
+        for a, b in zip(rb, ra):
+            assert a["numVertices"] == b["numVertices"] and a["numTriangles"] == b["numTriangles"]
+            assert V0[a["vertexOffset"]:a["vertexOffset"] + a["numVertices"]].tobytes() == V1[b["vertexOffset"]:b["vertexOffset"] + b["numVertices"]].tobytes()
+            assert T0[a["triangleOffset"]:a["triangleOffset"] + a["numTriangles"]].tobytes() == T1[b["triangleOffset"]:b["triangleOffset"] + b["numTriangles"]].tobytes()
     finally:
         ctx.destroy()
