@@ -115,11 +115,23 @@ def test_async_device_batch_counts_first(lc):
             else:
                 assert ctx.wait() == 0
             assert per_chunk(res, dv, dt, ds) == want
-        # the next call of any kind is ordered behind an unfinished one
-        rc, res, view = ctx.generateBatchDeviceAsync(ms)
+        # the next call of any kind is ordered behind an unfinished one: back-to-back counts-first calls on other
+        # chunk lists, no wait in between, and the last one's arenas hold what a synchronous call delivers
+        sub = ms[192:320]
+        rc, res_s, view_s = ctx.generateBatchDevice(sub)
         assert rc == 0
-        rc, res2, view2 = ctx.generateBatchDevice(ms[:64])
-        assert rc == 0 and (res2["numVertices"] == res0["numVertices"][:64]).all()
+        want_sub = per_chunk(res_s, *arenas(res_s, view_s))
+        for _ in range(3):
+            assert ctx.generateBatchDeviceAsync(ms)[0] == 0
+            assert ctx.generateBatchDeviceAsync(ms[:64])[0] == 0
+            rc, res2, view2 = ctx.generateBatchDeviceAsync(sub)
+            assert rc == 0
+            assert ctx.wait() == 0
+            assert per_chunk(res2, *arenas(res2, view2)) == want_sub
+        rc, res3, view3 = ctx.generateBatchDeviceAsync(ms)
+        assert rc == 0
+        rc, res4, view4 = ctx.generateBatchDevice(ms[:64])
+        assert rc == 0 and (res4["numVertices"] == res0["numVertices"][:64]).all()
     finally:
         ctx.destroy()
 
